@@ -1,0 +1,130 @@
+/* smo_b200.h - C ABI of the B200-native SphereManOpt hot path (libsmo_b200.so).
+ *
+ * Every entry point replaces one piece of the reference's Python/Dedalus hot path (citations are into the
+ * reference repository mannixp/SphereManOpt; SH = Example_Problems/Periodic_Domain(Fourier)/Swift_Hohenberg/
+ * FWD_Solve_SH23.py, KD = .../Kinematic_Dynamo/FWD_Solve_KDyn.py, SGD = Sphere_Grad_Descent.py).
+ *
+ * Conventions
+ *  - all functions return 0 on success or a negative error code; smo_last_error() gives the message of the
+ *    calling thread's last failure (the Python wrappers raise RuntimeError with it);
+ *  - pointers named *_dev are device pointers on the handle's device, *_host are host pointers; no library
+ *    types appear in the signatures, `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *  - vectors use the reference's layout: the dealiased grid in C order, float64.  SH23: M = 2*Npts values per
+ *    instance (SH:110-128).  Kinematic dynamo: concat(Fx.ravel(), Fy.ravel(), Fz.ravel()), 3*M^3 values with
+ *    M = 3*Npts/2 (KD:137); with more than one rank every rank holds the z-slab [x][y][z0:z0+nz] of each
+ *    component (3*M*M*nz values);
+ *  - handles are not thread safe; use one handle per thread.  No global mutable state besides the CUDA context.
+ */
+#ifndef SMO_B200_H
+#define SMO_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smo_sh23 smo_sh23_t;
+typedef struct smo_kdyn smo_kdyn_t;
+
+int smo_version(void);
+const char* smo_last_error(void);
+/* number of kernels of this library launched by the calling process so far (bench.py's gpu_launches) */
+long long smo_launch_count(void);
+
+/* flags */
+#define SMO_ADJOINT_CONTINUOUS 1 /* Adjoint_type="Continuous" (SH:654-656, KD:904-910) */
+#define SMO_COST_INTEGRATED 2    /* Cost_function="Integrated" (KD:655-669); not implemented yet: returns an error */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Swift-Hohenberg SH23 (1-D periodic Fourier, SBDF1, dealias 2)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Replaces FWD_Solve_Build_Lin (SH:279-332): Npts Fourier modes on [0,L), parameter a (= -0.3 at SH:309). */
+int smo_sh23_create(smo_sh23_t** h, int Npts, double L, double a);
+int smo_sh23_destroy(smo_sh23_t* h);
+/* bytes of snapshot storage per instance for n_iters steps: (n_iters+1)*(Npts/2) complex128 (GEN_BUFFER, SH:238-272) */
+size_t smo_sh23_snapshot_bytes(const smo_sh23_t* h, int n_iters);
+/* Replaces FWD_Solve_IVP_Lin (SH:409-545) for `batch` independent instances.
+ * X_dev [batch][M] in; snaps_dev [batch][n_iters+1][Npts/2] complex128 out; J_dev [batch] out with
+ * J = dt*sum_{n=0..n_iters} mean(u_n^2)  (the reference returns -J, SH:545). */
+int smo_sh23_forward(smo_sh23_t* h, const double* X_dev, int batch, double dt, int n_iters, void* snaps_dev,
+                     double* J_dev, void* stream);
+/* Replaces Compatib_Cond + ADJ_Solve_IVP_Lin (SH:552-596, 598-729).  snaps_dev as written by smo_sh23_forward;
+ * grad_dev [batch][M] out (dJ/du0 of the returned -J).  flags: SMO_ADJOINT_CONTINUOUS. */
+int smo_sh23_adjoint(smo_sh23_t* h, int batch, double dt, int n_iters, const void* snaps_dev, double* grad_dev,
+                     int flags, void* stream);
+/* Replaces FWD_Solve_IVP_PREP (SH:334-407): n_iters+1 SBDF1 steps, final state on the grid -> out_dev [batch][M]. */
+int smo_sh23_prep(smo_sh23_t* h, const double* X_dev, int batch, double dt, int n_iters, double* out_dev,
+                  void* stream);
+/* Host-buffer forms of the three calls above (copies inside, synchronous on return): the drop-in for the
+ * reference's numpy-in / numpy-out callables.  The snapshot store stays on the device inside the handle. */
+int smo_sh23_forward_host(smo_sh23_t* h, const double* X_host, int batch, double dt, int n_iters, double* J_host,
+                          void* stream);
+int smo_sh23_adjoint_host(smo_sh23_t* h, int batch, double dt, int n_iters, double* grad_host, int flags,
+                          void* stream);
+/* copy the handle-owned snapshot store of the last *_host forward to the host ([batch][n_iters+1][Npts/2] complex128) */
+int smo_sh23_snapshots_to_host(smo_sh23_t* h, int batch, int n_iters, void* snaps_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Kinematic dynamo (3-D periodic Fourier, CNAB1, dealias 3/2), slab-decomposed over nranks GPUs
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Replaces FWD_Solve_Build_Lin (KD:362-450) and the solver construction in ADJ_Solve_IVP_Lin (KD:807-886).
+ * rank/nranks: coefficient space is split along kx (Npts/2 planes), grid space along z; nranks must divide
+ * Npts/2 and 3*Npts/2.  nccl_comm: an initialised ncclComm_t (as void*) when nranks > 1, else NULL. */
+int smo_kdyn_create(smo_kdyn_t** h, int Npts, double L, int rank, int nranks, void* nccl_comm);
+int smo_kdyn_destroy(smo_kdyn_t* h);
+/* local sizes: elements of one grid component (M*M*nz doubles), of one coefficient component (complex128),
+ * and bytes of the snapshot store for n_iters steps = (n_iters+1)*3*coef_elems*16 (GEN_BUFFER, KD:319-355) */
+size_t smo_kdyn_grid_elems(const smo_kdyn_t* h);
+size_t smo_kdyn_coef_elems(const smo_kdyn_t* h);
+size_t smo_kdyn_snapshot_bytes(const smo_kdyn_t* h, int n_iters);
+/* Replaces FWD_Solve_IVP_Lin (KD:529-689), Cost_function="Final".  B0_dev, U_dev: [3][grid_elems] local slabs.
+ * snaps_dev out.  J_host out: this rank's share of mean_grid(|B_N|^2) (sum over ranks = J; reference returns -J). */
+int smo_kdyn_forward(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, double Rm, double dt, int n_iters,
+                     void* snaps_dev, double* J_host, int flags, void* stream);
+/* Replaces Compatib_Cond + ADJ_Solve_IVP_Lin (KD:696-764, 766-1004).  Uses the velocity field cached by the
+ * preceding smo_kdyn_forward on the same handle (the reference's f -> Grad_f state coupling).
+ * gradB_dev, gradU_dev: [3][grid_elems] out. */
+int smo_kdyn_adjoint(smo_kdyn_t* h, double Rm, double dt, int n_iters, const void* snaps_dev, double* gradB_dev,
+                     double* gradU_dev, int flags, void* stream);
+/* Replaces FWD_Solve_IVP_Prep (KD:452-527): n_iters+1 CNAB1 steps from B0 with velocity U; the final field on
+ * the grid -> out_dev [3][grid_elems]. */
+int smo_kdyn_prep(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, double Rm, double dt, int n_iters,
+                  double* out_dev, void* stream);
+/* Host-buffer forms: full-size reference vectors (3*M^3 doubles) on the host; each rank reads/writes its z-slab.
+ * The snapshot store is owned by the handle.  Synchronous on return. */
+int smo_kdyn_forward_host(smo_kdyn_t* h, const double* B0_host, const double* U_host, double Rm, double dt,
+                          int n_iters, double* J_host, int flags, void* stream);
+int smo_kdyn_adjoint_host(smo_kdyn_t* h, double Rm, double dt, int n_iters, double* gradB_host, double* gradU_host,
+                          int flags, void* stream);
+/* transform helpers (tests, initial conditions): grid [3][grid_elems] <-> coefficients [3][coef_elems] */
+int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid_dev, void* coef_dev, void* stream);
+int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef_dev, double* grid_dev, void* stream);
+/* per-kernel timing of the time loops: which = 0 off, 1..5 = z-pass, y-pass, fused x-pass, epilogue, all-to-all.
+ * smo_kdyn_profile_read returns the accumulated CUDA-event time (ms) and launch count since the last set. */
+int smo_kdyn_profile_set(smo_kdyn_t* h, int which);
+int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long* launches);
+/* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
+int smo_kdyn_use_graph(smo_kdyn_t* h, int on);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Inner product and sphere geometry on device vectors (rows A5/B5 and C1-C3)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* bytes of device workspace needed by the reductions below for vectors of n elements */
+size_t smo_vec_work_bytes(long long n);
+/* Replaces Inner_Prod / Inner_Prod_3 (SH:158-172, KD:173-181): *out_host = scale * sum_j x_j*y_j (scale = 1/M or
+ * 1/M^3 gives the reference's grid mean).  Deterministic; synchronises the stream. */
+int smo_vec_dot(const double* x_dev, const double* y_dev, long long n, double scale, double* out_host,
+                void* work_dev, void* stream);
+/* out = a*x + b*y (y may be NULL when b == 0): the numpy algebra of SGD:642, 659, 687-690, 772, 776 */
+int smo_vec_axpby(double a, const double* x_dev, double b, const double* y_dev, double* out_dev, long long n,
+                  void* stream);
+/* Replaces tangent_vector / transport_vector (SGD:625-659): out = v - (<x,v>/<x,x>) x, no host round trip */
+int smo_vec_project(const double* x_dev, const double* v_dev, double* out_dev, long long n, void* work_dev,
+                    void* stream);
+/* Replaces Update_vector (SGD:661-690): f = x + alpha*d ; out = f*sqrt(M0/(scale*sum f_j^2)) */
+int smo_vec_retract(const double* x_dev, double alpha, const double* d_dev, double M0, double scale, double* out_dev,
+                    long long n, void* work_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMO_B200_H */

@@ -1,0 +1,918 @@
+// C ABI of libsmo_b200.so (see include/smo_b200.h).  Host-side plans and launch sequences; all arithmetic
+// lives in the kernels of fft_pass.cuh, xpass.cuh, kd_epilogue.cuh, sh23.cuh and reduce.cuh.
+//
+// Built two ways from this one source:
+//   nvcc -gencode arch=compute_100a,code=sm_100a ...            -> libsmo_b200.so (the product)
+//   g++ -x c++ -DSMO_EMUL ...                                   -> tests/emul/_build/libsmo_emul.so, a host
+//        emulation of the same kernel bodies used ONLY by the CPU test-suite to check index logic without a GPU.
+#include "../../include/smo_b200.h"
+#include "fft_pass.cuh"
+#include "xpass.cuh"
+#include "kd_epilogue.cuh"
+#include "sh23.cuh"
+#include "reduce.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <atomic>
+
+#if !defined(SMO_EMUL) && defined(SMO_WITH_NCCL)
+#include <nccl.h>
+#endif
+
+using namespace smo;
+
+// ------------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define SMO_E_ARG -1
+#define SMO_E_CUDA -2
+#define SMO_E_UNSUPPORTED -3
+#define SMO_E_STATE -4
+#define SMO_E_COMM -5
+
+// ------------------------------------------------------------------------------------------------------------
+// runtime abstraction (CUDA or host emulation)
+// ------------------------------------------------------------------------------------------------------------
+#if defined(SMO_EMUL)
+typedef void* rt_stream;
+static int rt_malloc(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : fail(SMO_E_CUDA, "calloc(%zu) failed", n); }
+static void rt_free(void* p) { free(p); }
+static int rt_h2d(void* d, const void* s, size_t n, rt_stream) { memcpy(d, s, n); return 0; }
+static int rt_d2h(void* d, const void* s, size_t n, rt_stream) { memcpy(d, s, n); return 0; }
+static int rt_d2d(void* d, const void* s, size_t n, rt_stream) { memmove(d, s, n); return 0; }
+static int rt_copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, int, rt_stream) {
+  for (size_t r = 0; r < h; ++r) memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
+  return 0;
+}
+static int rt_memset(void* d, int v, size_t n, rt_stream) { memset(d, v, n); return 0; }
+static int rt_sync(rt_stream) { return 0; }
+static int rt_check(const char*) { return 0; }
+template <class K> static int launch(const typename K::Params& p, rt_stream) {
+  if (p.nwork <= 0) return 0;
+  const int grid = p.nwork < 3 ? p.nwork : 3;   // > 1 work item per CTA exercises the persistent loop
+  emul_kernel<K>(grid, K::SMEM, p);
+  g_launches++;
+  return 0;
+}
+#else
+typedef cudaStream_t rt_stream;
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess) return fail(SMO_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+static int rt_malloc(void** p, size_t n) {
+  CUDA_TRY(cudaMalloc(p, n ? n : 1));
+  CUDA_TRY(cudaMemset(*p, 0, n ? n : 1));
+  return 0;
+}
+static void rt_free(void* p) { if (p) cudaFree(p); }
+static int rt_h2d(void* d, const void* s, size_t n, rt_stream st) { CUDA_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st)); return 0; }
+static int rt_d2h(void* d, const void* s, size_t n, rt_stream st) { CUDA_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st)); return 0; }
+static int rt_d2d(void* d, const void* s, size_t n, rt_stream st) { CUDA_TRY(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st)); return 0; }
+// kind: 0 = host->device, 1 = device->host
+static int rt_copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, int kind, rt_stream st) {
+  CUDA_TRY(cudaMemcpy2DAsync(d, dp, s, sp, w, h, kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+static int rt_memset(void* d, int v, size_t n, rt_stream st) { CUDA_TRY(cudaMemsetAsync(d, v, n, st)); return 0; }
+static int rt_sync(rt_stream st) { CUDA_TRY(cudaStreamSynchronize(st)); return 0; }
+static int rt_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SMO_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+static int g_num_sms = 0;
+template <class K> struct LaunchCfg {
+  static int blocks_per_sm() {
+    static int v = -1;
+    if (v < 0) {
+      if (K::SMEM > 48 * 1024)
+        cudaFuncSetAttribute(smo_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smo_kernel<K>, K::THREADS, K::SMEM);
+      v = nb > 0 ? nb : 1;
+    }
+    return v;
+  }
+};
+template <class K> static int launch(const typename K::Params& p, rt_stream st) {
+  if (p.nwork <= 0) return 0;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  // persistent-style grid: at most one resident wave (a multiple of the SM count), CTAs loop over work items
+  const long long cap = (long long)g_num_sms * LaunchCfg<K>::blocks_per_sm();
+  const int grid = (int)(p.nwork < cap ? p.nwork : cap);
+  smo_kernel<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+  g_launches++;
+  return rt_check("kernel launch");
+}
+#endif
+
+#define TRY(x)             \
+  do {                     \
+    int rc_ = (x);         \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+static cplx* make_twiddles(int M, int* rc) {
+  std::vector<cplx> t(M);
+  for (int m = 0; m < M; ++m) {
+    const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)M;
+    t[m].x = (double)cosl(a);
+    t[m].y = (double)(-sinl(a));
+  }
+  void* d = nullptr;
+  *rc = rt_malloc(&d, sizeof(cplx) * M);
+  if (*rc) return nullptr;
+  *rc = rt_h2d(d, t.data(), sizeof(cplx) * M, 0);
+  if (*rc == 0) *rc = rt_sync(0);
+  return (cplx*)d;
+}
+
+extern "C" int smo_version(void) { return 100; }
+extern "C" const char* smo_last_error(void) { return g_err.c_str(); }
+extern "C" long long smo_launch_count(void) { return g_launches.load(); }
+
+// ============================================================================================================
+// vector ops
+// ============================================================================================================
+static int vec_nwork(long long n) { return (int)((n + VCHUNK - 1) / VCHUNK); }
+
+extern "C" size_t smo_vec_work_bytes(long long n) { return sizeof(double) * (2 * (size_t)vec_nwork(n) + 8); }
+
+template <int OP>
+static int vec_launch(const double* x, const double* y, double* out, long long n, double a, double b, double c,
+                      double* work, rt_stream st) {
+  VecParams p;
+  memset(&p, 0, sizeof p);
+  p.x = x; p.y = y; p.out = out; p.n = n; p.a = a; p.b = b; p.c = c;
+  p.nwork = vec_nwork(n); p.nsteps = 1;
+  p.partials = work ? work + 8 : nullptr;
+  p.scalars = work;
+  return launch<VecKernel<OP>>(p, st);
+}
+static int final_sum(double* work, long long n, int nq, double a, rt_stream st) {
+  SumParams s;
+  s.partials = work + 8; s.out = work; s.nwork = nq; s.nsteps = 1; s.npart = vec_nwork(n); s.nq = nq; s.a = a;
+  return launch<FinalSum>(s, st);
+}
+
+extern "C" int smo_vec_dot(const double* x, const double* y, long long n, double scale, double* out_host, void* work,
+                           void* stream) {
+  if (!x || !y || !out_host || !work || n <= 0) return fail(SMO_E_ARG, "smo_vec_dot: bad argument");
+  rt_stream st = (rt_stream)stream;
+  double* w = (double*)work;
+  TRY((vec_launch<V_DOT>(x, y, nullptr, n, 0, 0, 0, w, st)));
+  TRY(final_sum(w, n, 1, scale, st));
+  TRY(rt_d2h(out_host, w, sizeof(double), st));
+  return rt_sync(st);
+}
+extern "C" int smo_vec_axpby(double a, const double* x, double b, const double* y, double* out, long long n,
+                             void* stream) {
+  if (!x || !out || n <= 0 || (!y && b != 0.0)) return fail(SMO_E_ARG, "smo_vec_axpby: bad argument");
+  rt_stream st = (rt_stream)stream;
+  if (!y) return vec_launch<V_SCALE>(x, nullptr, out, n, a, 0, 0, nullptr, st);
+  return vec_launch<V_AXPBY>(x, y, out, n, a, b, 0, nullptr, st);
+}
+extern "C" int smo_vec_project(const double* x, const double* v, double* out, long long n, void* work, void* stream) {
+  if (!x || !v || !out || !work || n <= 0) return fail(SMO_E_ARG, "smo_vec_project: bad argument");
+  rt_stream st = (rt_stream)stream;
+  double* w = (double*)work;
+  TRY((vec_launch<V_DOT2>(x, v, nullptr, n, 0, 0, 0, w, st)));   // s0 = <x,v>, s1 = <x,x>
+  TRY(final_sum(w, n, 2, 1.0, st));
+  return vec_launch<V_PROJ>(x, v, out, n, 0, 0, 0, w, st);
+}
+extern "C" int smo_vec_retract(const double* x, double alpha, const double* d, double M0, double scale, double* out,
+                               long long n, void* work, void* stream) {
+  if (!x || !d || !out || !work || n <= 0) return fail(SMO_E_ARG, "smo_vec_retract: bad argument");
+  rt_stream st = (rt_stream)stream;
+  double* w = (double*)work;
+  TRY((vec_launch<V_AXPY_NRM>(x, d, out, n, alpha, 0, 0, w, st)));
+  TRY(final_sum(w, n, 1, 1.0, st));
+  return vec_launch<V_RESCALE>(nullptr, nullptr, out, n, 0, M0, scale, w, st);
+}
+
+// ============================================================================================================
+// SH23
+// ============================================================================================================
+struct smo_sh23 {
+  int N, M, H, Nh;
+  double L, a;
+  cplx *twH, *twM;
+  // handle-owned buffers of the *_host entry points
+  double* xin; double* jout; double* gout; cplx* snaps;
+  size_t cap_batch, cap_snap;
+};
+
+constexpr int SH_NI = 4;
+
+template <int H> static int sh23_run(smo_sh23* h, bool adj, Sh23Params& p, rt_stream st) {
+  typedef typename FacOf<H>::type F;
+  if (adj) return launch<Sh23Adj<F, SH_NI>>(p, st);
+  return launch<Sh23Fwd<F, SH_NI>>(p, st);
+}
+static int sh23_dispatch(smo_sh23* h, bool adj, Sh23Params& p, rt_stream st) {
+  p.nwork = (p.batch + SH_NI - 1) / SH_NI;
+  p.Nh = h->Nh; p.a = h->a; p.kfac = 2.0 * 3.14159265358979323846 / h->L;
+  p.twH = h->twH; p.twM = h->twM;
+  switch (h->H) {
+    case 64: return sh23_run<64>(h, adj, p, st);
+    case 128: return sh23_run<128>(h, adj, p, st);
+    case 256: return sh23_run<256>(h, adj, p, st);
+    default: return fail(SMO_E_UNSUPPORTED, "SH23: Npts=%d not supported (64, 128, 256)", h->N);
+  }
+}
+
+extern "C" int smo_sh23_create(smo_sh23_t** out, int Npts, double L, double a) {
+  if (!out) return fail(SMO_E_ARG, "smo_sh23_create: null handle pointer");
+  if (Npts != 64 && Npts != 128 && Npts != 256) return fail(SMO_E_UNSUPPORTED, "SH23: Npts=%d not supported (64, 128, 256)", Npts);
+  if (!(L > 0)) return fail(SMO_E_ARG, "SH23: L must be positive");
+  smo_sh23* h = new smo_sh23();
+  memset(h, 0, sizeof *h);
+  h->N = Npts; h->M = 2 * Npts; h->H = Npts; h->Nh = Npts / 2; h->L = L; h->a = a;
+  int rc = 0;
+  h->twH = make_twiddles(h->H, &rc);
+  if (rc == 0) h->twM = make_twiddles(h->M, &rc);
+  if (rc) { smo_sh23_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+extern "C" int smo_sh23_destroy(smo_sh23_t* h) {
+  if (!h) return 0;
+  rt_free(h->twH); rt_free(h->twM); rt_free(h->xin); rt_free(h->jout); rt_free(h->gout); rt_free(h->snaps);
+  delete h;
+  return 0;
+}
+extern "C" size_t smo_sh23_snapshot_bytes(const smo_sh23_t* h, int n_iters) {
+  return h ? sizeof(cplx) * (size_t)(n_iters + 1) * h->Nh : 0;
+}
+static int sh23_args(smo_sh23* h, int batch, double dt, int n_iters, const char* who) {
+  if (!h) return fail(SMO_E_ARG, "%s: null handle", who);
+  if (batch <= 0 || n_iters < 0 || !(dt > 0)) return fail(SMO_E_ARG, "%s: bad batch/dt/n_iters", who);
+  return 0;
+}
+extern "C" int smo_sh23_forward(smo_sh23_t* h, const double* X, int batch, double dt, int n_iters, void* snaps,
+                                double* J, void* stream) {
+  TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_forward"));
+  if (!X || !snaps || !J) return fail(SMO_E_ARG, "smo_sh23_forward: null buffer");
+  Sh23Params p;
+  memset(&p, 0, sizeof p);
+  p.X = X; p.snaps = (cplx*)snaps; p.J = J; p.batch = batch; p.n_iters = n_iters; p.dt = dt; p.flags = 0;
+  p.nsteps = n_iters + 3;
+  return sh23_dispatch(h, false, p, (rt_stream)stream);
+}
+extern "C" int smo_sh23_prep(smo_sh23_t* h, const double* X, int batch, double dt, int n_iters, double* out,
+                             void* stream) {
+  TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_prep"));
+  if (!X || !out) return fail(SMO_E_ARG, "smo_sh23_prep: null buffer");
+  Sh23Params p;
+  memset(&p, 0, sizeof p);
+  p.X = X; p.grad = out; p.batch = batch; p.n_iters = n_iters; p.dt = dt; p.flags = 2;
+  p.nsteps = n_iters + 3;
+  return sh23_dispatch(h, false, p, (rt_stream)stream);
+}
+extern "C" int smo_sh23_adjoint(smo_sh23_t* h, int batch, double dt, int n_iters, const void* snaps, double* grad,
+                                int flags, void* stream) {
+  TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_adjoint"));
+  if (!snaps || !grad) return fail(SMO_E_ARG, "smo_sh23_adjoint: null buffer");
+  Sh23Params p;
+  memset(&p, 0, sizeof p);
+  p.snaps = (cplx*)snaps; p.grad = grad; p.batch = batch; p.n_iters = n_iters; p.dt = dt;
+  p.flags = (flags & SMO_ADJOINT_CONTINUOUS) ? 1 : 0;
+  p.nsteps = n_iters + 2;
+  return sh23_dispatch(h, true, p, (rt_stream)stream);
+}
+static int sh23_reserve(smo_sh23* h, int batch, int n_iters) {
+  if ((size_t)batch > h->cap_batch) {
+    rt_free(h->xin); rt_free(h->jout); rt_free(h->gout);
+    h->xin = h->jout = h->gout = nullptr; h->cap_batch = 0;
+    TRY(rt_malloc((void**)&h->xin, sizeof(double) * batch * h->M));
+    TRY(rt_malloc((void**)&h->gout, sizeof(double) * batch * h->M));
+    TRY(rt_malloc((void**)&h->jout, sizeof(double) * batch));
+    h->cap_batch = batch;
+  }
+  const size_t need = smo_sh23_snapshot_bytes(h, n_iters) * batch;
+  if (need > h->cap_snap) {
+    rt_free(h->snaps); h->snaps = nullptr; h->cap_snap = 0;
+    TRY(rt_malloc((void**)&h->snaps, need));
+    h->cap_snap = need;
+  }
+  return 0;
+}
+extern "C" int smo_sh23_forward_host(smo_sh23_t* h, const double* X, int batch, double dt, int n_iters, double* J,
+                                     void* stream) {
+  TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_forward_host"));
+  if (!X || !J) return fail(SMO_E_ARG, "smo_sh23_forward_host: null buffer");
+  rt_stream st = (rt_stream)stream;
+  TRY(sh23_reserve(h, batch, n_iters));
+  TRY(rt_h2d(h->xin, X, sizeof(double) * batch * h->M, st));
+  TRY(smo_sh23_forward(h, h->xin, batch, dt, n_iters, h->snaps, h->jout, stream));
+  TRY(rt_d2h(J, h->jout, sizeof(double) * batch, st));
+  return rt_sync(st);
+}
+extern "C" int smo_sh23_adjoint_host(smo_sh23_t* h, int batch, double dt, int n_iters, double* grad, int flags,
+                                     void* stream) {
+  TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_adjoint_host"));
+  if (!grad) return fail(SMO_E_ARG, "smo_sh23_adjoint_host: null buffer");
+  if (!h->snaps || (size_t)batch > h->cap_batch || smo_sh23_snapshot_bytes(h, n_iters) * batch > h->cap_snap)
+    return fail(SMO_E_STATE, "smo_sh23_adjoint_host: no matching forward solve on this handle");
+  rt_stream st = (rt_stream)stream;
+  TRY(smo_sh23_adjoint(h, batch, dt, n_iters, h->snaps, h->gout, flags, stream));
+  TRY(rt_d2h(grad, h->gout, sizeof(double) * batch * h->M, st));
+  return rt_sync(st);
+}
+extern "C" int smo_sh23_snapshots_to_host(smo_sh23_t* h, int batch, int n_iters, void* out, void* stream) {
+  if (!h || !out || !h->snaps) return fail(SMO_E_STATE, "smo_sh23_snapshots_to_host: no snapshots");
+  rt_stream st = (rt_stream)stream;
+  TRY(rt_d2h(out, h->snaps, smo_sh23_snapshot_bytes(h, n_iters) * batch, st));
+  return rt_sync(st);
+}
+
+// ============================================================================================================
+// kinematic dynamo
+// ============================================================================================================
+struct smo_kdyn {
+  int N, M, Nh, Nc, kmax, Pc;
+  double L, kfac;
+  int rank, nranks, nkx, kx0, nz, z0;
+  size_t csize, p1size, p2size, gsize;
+  cplx* tw;
+  cplx* p1[MAXF];    // [s][nkx][Nc][nz] (kx-slab side of the transpose)
+  cplx* p1t[MAXF];   // [Nh][Nc][nz]     (z-slab side; aliases p1 on one rank)
+  cplx* p2[MAXF];    // [Nh][M][nz]
+  cplx* cw[MAXF];    // coefficient work
+  cplx* G[3]; cplx* NU[3]; cplx* W[3];
+  double* Ug[3];     // projected velocity on the grid [M][M][nz]
+  double* gwork;     // 3*gsize doubles
+  double* vwork;     // reduction workspace
+  bool have_U;
+  // handle-owned buffers of the *_host entry points
+  double* hB; double* hU; double* hGB; double* hGU; cplx* snaps; size_t cap_snap;
+  void* comm;
+  // profiling
+  int prof_which; double prof_ms; long long prof_n;
+#if !defined(SMO_EMUL)
+  std::vector<cudaEvent_t>* ev;
+  size_t ev_used;
+#endif
+  int use_graph;
+};
+
+enum { PK_Z = 1, PK_Y = 2, PK_X = 3, PK_EPI = 4, PK_A2A = 5 };
+
+#if !defined(SMO_EMUL)
+static void prof_begin(smo_kdyn* h, int kind, rt_stream st) {
+  if (h->prof_which != kind) return;
+  if (h->ev_used + 2 > h->ev->size()) {
+    for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev->push_back(e); }
+  }
+  cudaEventRecord((*h->ev)[h->ev_used], st);
+}
+static void prof_end(smo_kdyn* h, int kind, rt_stream st) {
+  if (h->prof_which != kind) return;
+  cudaEventRecord((*h->ev)[h->ev_used + 1], st);
+  h->ev_used += 2;
+}
+static void prof_collect(smo_kdyn* h, rt_stream st) {
+  if (!h->prof_which || h->ev_used == 0) return;
+  cudaStreamSynchronize(st);
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, (*h->ev)[i], (*h->ev)[i + 1]) == cudaSuccess) { h->prof_ms += ms; h->prof_n++; }
+  }
+  h->ev_used = 0;
+}
+#else
+static void prof_begin(smo_kdyn*, int, rt_stream) {}
+static void prof_end(smo_kdyn*, int, rt_stream) {}
+static void prof_collect(smo_kdyn*, rt_stream) {}
+#endif
+
+// ---- all-to-all transposes between the kx-slab layout p1 and the z-slab layout p1t -------------------------
+// p1  = [s][nkx][Nc][nz] : block s goes to rank s;  p1t = [s][nkx][Nc][nz] read as [Nh][Nc][nz] : block s came
+// from rank s.  Both directions exchange equal contiguous blocks of nkx*Nc*nz complex numbers per peer.
+#if defined(SMO_EMUL)
+typedef void (*smo_emul_a2a_fn)(const void* send, void* recv, long long bytes_per_peer, void* user);
+struct EmulComm { smo_emul_a2a_fn fn; void* user; };
+#endif
+static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_stream st) {
+  if (h->nranks == 1) return 0;
+  const size_t blk = (size_t)h->nkx * h->Nc * h->nz;
+#if defined(SMO_EMUL)
+  EmulComm* c = (EmulComm*)h->comm;
+  for (int f = 0; f < nf; ++f) c->fn(src[f], dst[f], (long long)(blk * sizeof(cplx)), c->user);
+  return 0;
+#elif defined(SMO_WITH_NCCL)
+  ncclComm_t comm = (ncclComm_t)h->comm;
+  prof_begin(h, PK_A2A, st);
+  if (ncclGroupStart() != ncclSuccess) return fail(SMO_E_COMM, "ncclGroupStart failed");
+  for (int f = 0; f < nf; ++f)
+    for (int s = 0; s < h->nranks; ++s) {
+      ncclResult_t r1 = ncclSend(src[f] + blk * s, blk * 2, ncclDouble, s, comm, st);
+      ncclResult_t r2 = ncclRecv(dst[f] + blk * s, blk * 2, ncclDouble, s, comm, st);
+      if (r1 != ncclSuccess || r2 != ncclSuccess) { ncclGroupEnd(); return fail(SMO_E_COMM, "ncclSend/Recv failed: %s", ncclGetErrorString(r1 != ncclSuccess ? r1 : r2)); }
+    }
+  ncclResult_t r = ncclGroupEnd();
+  if (r != ncclSuccess) return fail(SMO_E_COMM, "ncclGroupEnd failed: %s", ncclGetErrorString(r));
+  prof_end(h, PK_A2A, st);
+  return 0;
+#else
+  (void)src; (void)dst; (void)nf; (void)st; (void)blk;
+  return fail(SMO_E_UNSUPPORTED, "library built without NCCL: nranks must be 1");
+#endif
+}
+
+// ---- pass launchers ---------------------------------------------------------------------------------------
+template <int M> struct KdOps {
+  typedef typename FacOf<M>::type F;
+  static constexpr int TZ = 8;    // lines per CTA, contiguous (z) passes
+  static constexpr int TY = 8;    // lines per CTA, strided (y) passes
+  static constexpr int TX = 8;    // columns per CTA, x passes with <= 3 fields
+  static constexpr int TXA = 4;   // columns per CTA, fused adjoint x pass (6 fields)
+
+  static void fill(PassParams& p, smo_kdyn* h, int nf) {
+    memset(&p, 0, sizeof p);
+    p.nfields = nf; p.nsteps = 1; p.kmax = h->kmax; p.tw = h->tw; p.scale = 1.0;
+    p.in_split = p.out_split = M; p.in_blk = p.out_blk = 0;
+  }
+  // coefficient [nkx][Nc][Pc] -> p1 [s][nkx][Nc][nz]   (zero-pad + inverse FFT along z)
+  static int inv_z(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
+    PassParams p; fill(p, h, nf);
+    for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
+    p.pad = 1; p.nA = 1; p.nB = h->nkx * h->Nc; p.tilesB = (p.nB + TZ - 1) / TZ;
+    p.in_sA = 0; p.in_sB = h->Pc; p.in_sN = 1;
+    p.out_sA = 0; p.out_sB = h->nz; p.out_sN = 1; p.out_split = h->nz; p.out_blk = (long long)h->nkx * h->Nc * h->nz;
+    p.nwork = nf * p.nA * p.tilesB;
+    prof_begin(h, PK_Z, st);
+    int rc = launch<FftPass<F, +1, false, TZ>>(p, st);
+    prof_end(h, PK_Z, st);
+    return rc;
+  }
+  // p1 [s][nkx][Nc][nz] -> coefficient   (forward FFT along z + truncation), scaled by 1/M
+  static int fwd_z(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
+    PassParams p; fill(p, h, nf);
+    for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
+    p.pad = 0; p.nA = 1; p.nB = h->nkx * h->Nc; p.tilesB = (p.nB + TZ - 1) / TZ;
+    p.in_sA = 0; p.in_sB = h->nz; p.in_sN = 1; p.in_split = h->nz; p.in_blk = (long long)h->nkx * h->Nc * h->nz;
+    p.out_sA = 0; p.out_sB = h->Pc; p.out_sN = 1;
+    p.scale = 1.0 / M;
+    p.nwork = nf * p.nA * p.tilesB;
+    prof_begin(h, PK_Z, st);
+    int rc = launch<FftPass<F, -1, false, TZ>>(p, st);
+    prof_end(h, PK_Z, st);
+    return rc;
+  }
+  // p1t [Nh][Nc][nz] -> p2 [Nh][M][nz]   (zero-pad + inverse FFT along y)
+  static int inv_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
+    PassParams p; fill(p, h, nf);
+    for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
+    p.pad = 1; p.nA = h->Nh; p.nB = h->nz; p.tilesB = (p.nB + TY - 1) / TY;
+    p.in_sA = (long long)h->Nc * h->nz; p.in_sB = 1; p.in_sN = h->nz;
+    p.out_sA = (long long)M * h->nz; p.out_sB = 1; p.out_sN = h->nz;
+    p.nwork = nf * p.nA * p.tilesB;
+    prof_begin(h, PK_Y, st);
+    int rc = launch<FftPass<F, +1, true, TY>>(p, st);
+    prof_end(h, PK_Y, st);
+    return rc;
+  }
+  static int fwd_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
+    PassParams p; fill(p, h, nf);
+    for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
+    p.pad = 0; p.nA = h->Nh; p.nB = h->nz; p.tilesB = (p.nB + TY - 1) / TY;
+    p.in_sA = (long long)M * h->nz; p.in_sB = 1; p.in_sN = h->nz;
+    p.out_sA = (long long)h->Nc * h->nz; p.out_sB = 1; p.out_sN = h->nz;
+    p.scale = 1.0 / M;
+    p.nwork = nf * p.nA * p.tilesB;
+    prof_begin(h, PK_Y, st);
+    int rc = launch<FftPass<F, -1, true, TY>>(p, st);
+    prof_end(h, PK_Y, st);
+    return rc;
+  }
+  static void xfill(XParams& p, smo_kdyn* h, int T) {
+    memset(&p, 0, sizeof p);
+    p.nsteps = 1; p.ncols = (long long)M * h->nz; p.Nh = h->Nh; p.tw = h->tw; p.scale = 1.0 / M;
+    p.nwork = (int)(p.ncols / T);
+  }
+  static int x_c2r(smo_kdyn* h, const cplx* const* in, double* const* out, rt_stream st) {
+    XParams p; xfill(p, h, TX);
+    for (int f = 0; f < 3; ++f) { p.sin[f] = in[f]; p.gout[f] = out[f]; }
+    return launch<XPass<F, TX, X_C2R, 3, 3>>(p, st);
+  }
+  static int x_r2c(smo_kdyn* h, const double* const* in, cplx* const* out, rt_stream st) {
+    XParams p; xfill(p, h, TX);
+    for (int f = 0; f < 3; ++f) { p.gin[f] = in[f]; p.sout[f] = out[f]; }
+    return launch<XPass<F, TX, X_R2C, 3, 3>>(p, st);
+  }
+  static int x_fwd(smo_kdyn* h, cplx* const* io, rt_stream st) {
+    XParams p; xfill(p, h, TX);
+    for (int f = 0; f < 3; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; p.gin[f] = h->Ug[f]; }
+    prof_begin(h, PK_X, st);
+    int rc = launch<XPass<F, TX, X_FWD, 3, 3>>(p, st);
+    prof_end(h, PK_X, st);
+    return rc;
+  }
+  static int x_adj(smo_kdyn* h, cplx* const* io, rt_stream st) {
+    XParams p; xfill(p, h, TXA);
+    for (int f = 0; f < 6; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
+    for (int f = 0; f < 3; ++f) p.gin[f] = h->Ug[f];
+    prof_begin(h, PK_X, st);
+    int rc = launch<XPass<F, TXA, X_ADJ, 6, 6>>(p, st);
+    prof_end(h, PK_X, st);
+    return rc;
+  }
+
+  // grid [3][gsize] -> coefficients [3][csize]
+  static int to_coef(smo_kdyn* h, const double* grid, cplx* const* coef, rt_stream st) {
+    const double* g[3] = {grid, grid + h->gsize, grid + 2 * h->gsize};
+    TRY(x_r2c(h, g, h->p2, st));
+    TRY(fwd_y(h, h->p2, h->p1t, 3, st));
+    TRY(a2a(h, h->p1t, h->p1, 3, st));
+    return fwd_z(h, h->p1, coef, 3, st);
+  }
+  static int to_grid(smo_kdyn* h, const cplx* const* coef, double* grid, rt_stream st) {
+    double* g[3] = {grid, grid + h->gsize, grid + 2 * h->gsize};
+    TRY(inv_z(h, coef, h->p1, 3, st));
+    TRY(a2a(h, h->p1, h->p1t, 3, st));
+    TRY(inv_y(h, h->p1t, h->p2, 3, st));
+    return x_c2r(h, h->p2, g, st);
+  }
+  static void efill(EpiParams& p, smo_kdyn* h, double Rm, double dt, int flag) {
+    memset(&p, 0, sizeof p);
+    p.nsteps = 1; p.n = (long long)h->csize; p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
+    p.kfac = h->kfac; p.Rm = Rm; p.dt = dt; p.flag = flag;
+    p.nwork = (int)((p.n + 255) / 256);
+  }
+  // one CNAB1 step  Bn -> Bnp1 (both [3] coefficient arrays)
+  static int fwd_step(smo_kdyn* h, const cplx* const* Bn, cplx* const* Bnp1, double Rm, double dt, rt_stream st) {
+    TRY(inv_z(h, Bn, h->p1, 3, st));
+    TRY(a2a(h, h->p1, h->p1t, 3, st));
+    TRY(inv_y(h, h->p1t, h->p2, 3, st));
+    TRY(x_fwd(h, h->p2, st));
+    TRY(fwd_y(h, h->p2, h->p1t, 3, st));
+    TRY(a2a(h, h->p1t, h->p1, 3, st));
+    TRY(fwd_z(h, h->p1, h->cw, 3, st));
+    EpiParams e; efill(e, h, Rm, dt, 0);
+    for (int c = 0; c < 3; ++c) { e.a[c] = h->cw[c]; e.b[c] = Bn[c]; e.o[c] = Bnp1[c]; }
+    prof_begin(h, PK_EPI, st);
+    int rc = launch<EpiKernel<EPI_FWD>>(e, st);
+    prof_end(h, PK_EPI, st);
+    return rc;
+  }
+  // one adjoint step using forward state Bf (coefficients)
+  static int adj_step(smo_kdyn* h, const cplx* const* Bf, double Rm, double dt, int flag, rt_stream st) {
+    const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], Bf[0], Bf[1], Bf[2]};
+    TRY(inv_z(h, in6, h->p1, 6, st));
+    TRY(a2a(h, h->p1, h->p1t, 6, st));
+    TRY(inv_y(h, h->p1t, h->p2, 6, st));
+    TRY(x_adj(h, h->p2, st));
+    TRY(fwd_y(h, h->p2, h->p1t, 6, st));
+    TRY(a2a(h, h->p1t, h->p1, 6, st));
+    TRY(fwd_z(h, h->p1, h->cw, 6, st));
+    EpiParams e; efill(e, h, Rm, dt, flag);
+    for (int c = 0; c < 6; ++c) e.a[c] = h->cw[c];
+    for (int c = 0; c < 3; ++c) {
+      e.b[c] = h->G[c]; e.b[3 + c] = h->NU[c];
+      e.o[c] = h->G[c]; e.o[3 + c] = h->NU[c];
+      e.o2[c] = h->W[c]; e.o2[3 + c] = const_cast<cplx*>(Bf[c]);
+    }
+    prof_begin(h, PK_EPI, st);
+    int rc = launch<EpiKernel<EPI_ADJ>>(e, st);
+    prof_end(h, PK_EPI, st);
+    return rc;
+  }
+  static int compat(smo_kdyn* h, const cplx* const* BN, double Rm, double dt, int flag, rt_stream st) {
+    EpiParams e; efill(e, h, Rm, dt, flag);
+    for (int c = 0; c < 3; ++c) { e.b[c] = BN[c]; e.o[c] = h->G[c]; e.o2[c] = h->W[c]; }
+    return launch<EpiKernel<EPI_COMPAT>>(e, st);
+  }
+  static int final_scale(smo_kdyn* h, double Rm, double dt, int flag, rt_stream st) {
+    EpiParams e; efill(e, h, Rm, dt, flag);
+    for (int c = 0; c < 3; ++c) { e.b[c] = h->G[c]; e.o[c] = h->cw[c]; }
+    return launch<EpiKernel<EPI_FINAL>>(e, st);
+  }
+};
+
+static void snap_ptrs(smo_kdyn* h, void* snaps, int n, cplx** out) {
+  cplx* s = (cplx*)snaps;
+  for (int c = 0; c < 3; ++c) out[c] = s + ((size_t)n * 3 + c) * h->csize;
+}
+
+// loop bodies, templated on M ---------------------------------------------------------------------------------
+template <int M> static int kd_set_U(smo_kdyn* h, const double* U, rt_stream st) {
+  // parameter fields are projected on the retained modes at first use [D2-8]: to_coef then to_grid
+  TRY(KdOps<M>::to_coef(h, U, h->cw, st));
+  double* g = h->gwork;
+  TRY(KdOps<M>::to_grid(h, h->cw, g, st));
+  for (int c = 0; c < 3; ++c) TRY(rt_d2d(h->Ug[c], g + (size_t)c * h->gsize, sizeof(double) * h->gsize, st));
+  h->have_U = true;
+  return 0;
+}
+template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
+                                       void* snaps, double* J_host, rt_stream st) {
+  TRY(kd_set_U<M>(h, U, st));
+  cplx* s0[3]; cplx* s1[3];
+  snap_ptrs(h, snaps, 0, s0);
+  TRY(KdOps<M>::to_coef(h, B0, s0, st));
+  for (int n = 0; n < n_iters; ++n) {
+    snap_ptrs(h, snaps, n, s0);
+    snap_ptrs(h, snaps, n + 1, s1);
+    TRY(KdOps<M>::fwd_step(h, s0, s1, Rm, dt, st));
+  }
+  // Cost "Final": J = mean over the dealiased grid of |B^N|^2 (FWD_Solve_KDyn.py:622, 671-673)
+  snap_ptrs(h, snaps, n_iters, s0);
+  TRY(KdOps<M>::to_grid(h, s0, h->gwork, st));
+  const double scale = 1.0 / ((double)M * M * M);
+  prof_collect(h, st);
+  return smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st);
+}
+template <int M> static int kd_prep(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
+                                    double* out, rt_stream st) {
+  TRY(kd_set_U<M>(h, U, st));
+  // ping-pong between G and NU as coefficient state (no snapshots kept)
+  cplx** a = h->G; cplx** b = h->NU;
+  TRY(KdOps<M>::to_coef(h, B0, a, st));
+  for (int n = 0; n < n_iters + 1; ++n) {
+    TRY(KdOps<M>::fwd_step(h, a, b, Rm, dt, st));
+    cplx** t = a; a = b; b = t;
+  }
+  return KdOps<M>::to_grid(h, a, out, st);
+}
+template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_iters, const void* snaps, double* gB,
+                                       double* gU, int flags, rt_stream st) {
+  const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
+  cplx* s[3];
+  snap_ptrs(h, const_cast<void*>(snaps), n_iters, s);
+  TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
+  for (int c = 0; c < 3; ++c) TRY(rt_memset(h->NU[c], 0, sizeof(cplx) * h->csize, st));
+  for (int m = 0; m < n_iters; ++m) {
+    const int idx = cont ? (n_iters - m) : (n_iters - 1 - m);   // snapshot_index -1-m / -2-m
+    snap_ptrs(h, const_cast<void*>(snaps), idx, s);
+    TRY(KdOps<M>::adj_step(h, s, Rm, dt, 0, st));
+  }
+  TRY(KdOps<M>::final_scale(h, Rm, dt, cont, st));
+  TRY(KdOps<M>::to_grid(h, h->cw, gB, st));
+  TRY(KdOps<M>::to_grid(h, h->NU, gU, st));
+  prof_collect(h, st);
+  return 0;
+}
+
+#define KD_DISPATCH(h, CALL)                                                                       \
+  switch ((h)->M) {                                                                                \
+    case 24: return CALL<24>;                                                                      \
+    case 36: return CALL<36>;                                                                      \
+    case 48: return CALL<48>;                                                                      \
+    case 96: return CALL<96>;                                                                      \
+    case 192: return CALL<192>;                                                                    \
+    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", (h)->N);    \
+  }
+
+static bool kd_supported(int Npts) { return Npts == 16 || Npts == 24 || Npts == 32 || Npts == 64 || Npts == 128; }
+
+extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, int nranks, void* comm) {
+  if (!out) return fail(SMO_E_ARG, "smo_kdyn_create: null handle pointer");
+  if (!kd_supported(Npts)) return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported (16, 24, 32, 64, 128)", Npts);
+  if (!(L > 0) || nranks < 1 || rank < 0 || rank >= nranks) return fail(SMO_E_ARG, "smo_kdyn_create: bad L/rank/nranks");
+  const int M = 3 * Npts / 2, Nh = Npts / 2;
+  if (Nh % nranks || M % nranks) return fail(SMO_E_ARG, "nranks=%d must divide Npts/2=%d and 3*Npts/2=%d", nranks, Nh, M);
+  if (nranks > 1 && !comm) return fail(SMO_E_ARG, "smo_kdyn_create: nranks > 1 needs a communicator");
+  const int nz = M / nranks;
+  if (nz % 8) {
+    if (nranks > 1) return fail(SMO_E_ARG, "local z extent %d must be a multiple of 8", nz);
+  }
+  smo_kdyn* h = new smo_kdyn();
+  h->N = Npts; h->M = M; h->Nh = Nh; h->kmax = (Npts - 1) / 2; h->Nc = 2 * h->kmax + 1; h->Pc = h->Nc + 1;
+  h->L = L; h->kfac = 2.0 * 3.14159265358979323846 / L;
+  h->rank = rank; h->nranks = nranks; h->nkx = Nh / nranks; h->kx0 = rank * h->nkx; h->nz = nz; h->z0 = rank * nz;
+  h->csize = (size_t)h->nkx * h->Nc * h->Pc;
+  h->p1size = (size_t)h->nkx * h->Nc * M;
+  h->p2size = (size_t)Nh * M * nz;
+  h->gsize = (size_t)M * M * nz;
+  h->comm = comm;
+  h->have_U = false;
+  h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
+  h->hB = h->hU = h->hGB = h->hGU = nullptr; h->snaps = nullptr; h->cap_snap = 0;
+  h->tw = nullptr; h->gwork = nullptr; h->vwork = nullptr;
+  for (int f = 0; f < MAXF; ++f) h->p1[f] = h->p1t[f] = h->p2[f] = h->cw[f] = nullptr;
+  for (int c = 0; c < 3; ++c) { h->G[c] = h->NU[c] = h->W[c] = nullptr; h->Ug[c] = nullptr; }
+#if !defined(SMO_EMUL)
+  h->ev = new std::vector<cudaEvent_t>(); h->ev_used = 0;
+#endif
+  int rc = 0;
+  h->tw = make_twiddles(M, &rc);
+  for (int f = 0; f < MAXF && rc == 0; ++f) {
+    rc = rt_malloc((void**)&h->p1[f], sizeof(cplx) * h->p1size);
+    if (rc == 0) {
+      if (nranks > 1) rc = rt_malloc((void**)&h->p1t[f], sizeof(cplx) * h->p1size);
+      else h->p1t[f] = h->p1[f];
+    }
+    if (rc == 0) rc = rt_malloc((void**)&h->p2[f], sizeof(cplx) * h->p2size);
+    if (rc == 0) rc = rt_malloc((void**)&h->cw[f], sizeof(cplx) * h->csize);
+  }
+  for (int c = 0; c < 3 && rc == 0; ++c) {
+    rc = rt_malloc((void**)&h->G[c], sizeof(cplx) * h->csize);
+    if (rc == 0) rc = rt_malloc((void**)&h->NU[c], sizeof(cplx) * h->csize);
+    if (rc == 0) rc = rt_malloc((void**)&h->W[c], sizeof(cplx) * h->csize);
+    if (rc == 0) rc = rt_malloc((void**)&h->Ug[c], sizeof(double) * h->gsize);
+  }
+  if (rc == 0) rc = rt_malloc((void**)&h->gwork, sizeof(double) * 3 * h->gsize);
+  if (rc == 0) rc = rt_malloc((void**)&h->vwork, smo_vec_work_bytes((long long)(3 * h->gsize)));
+  if (rc) { smo_kdyn_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
+  if (!h) return 0;
+  rt_free(h->tw);
+  for (int f = 0; f < MAXF; ++f) {
+    if (h->nranks > 1) rt_free(h->p1t[f]);
+    rt_free(h->p1[f]); rt_free(h->p2[f]); rt_free(h->cw[f]);
+  }
+  for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); }
+  rt_free(h->gwork); rt_free(h->vwork);
+  rt_free(h->hB); rt_free(h->hU); rt_free(h->hGB); rt_free(h->hGU); rt_free(h->snaps);
+#if !defined(SMO_EMUL)
+  if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
+#endif
+  delete h;
+  return 0;
+}
+extern "C" size_t smo_kdyn_grid_elems(const smo_kdyn_t* h) { return h ? h->gsize : 0; }
+extern "C" size_t smo_kdyn_coef_elems(const smo_kdyn_t* h) { return h ? h->csize : 0; }
+extern "C" size_t smo_kdyn_snapshot_bytes(const smo_kdyn_t* h, int n_iters) {
+  return h ? sizeof(cplx) * 3 * h->csize * (size_t)(n_iters + 1) : 0;
+}
+static int kd_args(smo_kdyn* h, double Rm, double dt, int n_iters, int flags, const char* who) {
+  if (!h) return fail(SMO_E_ARG, "%s: null handle", who);
+  if (!(Rm > 0) || !(dt > 0) || n_iters < 0) return fail(SMO_E_ARG, "%s: bad Rm/dt/n_iters", who);
+  if (flags & SMO_COST_INTEGRATED) return fail(SMO_E_UNSUPPORTED, "%s: Cost_function=\"Integrated\" is not implemented", who);
+  return 0;
+}
+extern "C" int smo_kdyn_forward(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
+                                void* snaps, double* J_host, int flags, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward"));
+  if (!B0 || !U || !snaps || !J_host) return fail(SMO_E_ARG, "smo_kdyn_forward: null buffer");
+  rt_stream st = (rt_stream)stream;
+#define CALL_FWD kd_forward
+  switch (h->M) {
+    case 24: return kd_forward<24>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
+    case 36: return kd_forward<36>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
+    case 48: return kd_forward<48>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
+    case 96: return kd_forward<96>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
+    case 192: return kd_forward<192>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
+    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
+  }
+}
+extern "C" int smo_kdyn_prep(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
+                             double* out, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, 0, "smo_kdyn_prep"));
+  if (!B0 || !U || !out) return fail(SMO_E_ARG, "smo_kdyn_prep: null buffer");
+  rt_stream st = (rt_stream)stream;
+  switch (h->M) {
+    case 24: return kd_prep<24>(h, B0, U, Rm, dt, n_iters, out, st);
+    case 36: return kd_prep<36>(h, B0, U, Rm, dt, n_iters, out, st);
+    case 48: return kd_prep<48>(h, B0, U, Rm, dt, n_iters, out, st);
+    case 96: return kd_prep<96>(h, B0, U, Rm, dt, n_iters, out, st);
+    case 192: return kd_prep<192>(h, B0, U, Rm, dt, n_iters, out, st);
+    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
+  }
+}
+extern "C" int smo_kdyn_adjoint(smo_kdyn_t* h, double Rm, double dt, int n_iters, const void* snaps, double* gB,
+                                double* gU, int flags, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_adjoint"));
+  if (!snaps || !gB || !gU) return fail(SMO_E_ARG, "smo_kdyn_adjoint: null buffer");
+  if (!h->have_U) return fail(SMO_E_STATE, "smo_kdyn_adjoint: no preceding forward solve on this handle");
+  rt_stream st = (rt_stream)stream;
+  switch (h->M) {
+    case 24: return kd_adjoint<24>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
+    case 36: return kd_adjoint<36>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
+    case 48: return kd_adjoint<48>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
+    case 96: return kd_adjoint<96>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
+    case 192: return kd_adjoint<192>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
+    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
+  }
+}
+extern "C" int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid, void* coef, void* stream) {
+  if (!h || !grid || !coef) return fail(SMO_E_ARG, "smo_kdyn_to_coef: bad argument");
+  rt_stream st = (rt_stream)stream;
+  cplx* c[3] = {(cplx*)coef, (cplx*)coef + h->csize, (cplx*)coef + 2 * h->csize};
+  switch (h->M) {
+    case 24: return KdOps<24>::to_coef(h, grid, c, st);
+    case 36: return KdOps<36>::to_coef(h, grid, c, st);
+    case 48: return KdOps<48>::to_coef(h, grid, c, st);
+    case 96: return KdOps<96>::to_coef(h, grid, c, st);
+    case 192: return KdOps<192>::to_coef(h, grid, c, st);
+    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
+  }
+}
+extern "C" int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef, double* grid, void* stream) {
+  if (!h || !grid || !coef) return fail(SMO_E_ARG, "smo_kdyn_to_grid: bad argument");
+  rt_stream st = (rt_stream)stream;
+  const cplx* c[3] = {(const cplx*)coef, (const cplx*)coef + h->csize, (const cplx*)coef + 2 * h->csize};
+  switch (h->M) {
+    case 24: return KdOps<24>::to_grid(h, c, grid, st);
+    case 36: return KdOps<36>::to_grid(h, c, grid, st);
+    case 48: return KdOps<48>::to_grid(h, c, grid, st);
+    case 96: return KdOps<96>::to_grid(h, c, grid, st);
+    case 192: return KdOps<192>::to_grid(h, c, grid, st);
+    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
+  }
+}
+extern "C" int smo_kdyn_profile_set(smo_kdyn_t* h, int which) {
+  if (!h) return fail(SMO_E_ARG, "smo_kdyn_profile_set: null handle");
+  h->prof_which = which; h->prof_ms = 0; h->prof_n = 0;
+#if !defined(SMO_EMUL)
+  h->ev_used = 0;
+#endif
+  return 0;
+}
+extern "C" int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long* launches) {
+  if (!h) return fail(SMO_E_ARG, "smo_kdyn_profile_read: null handle");
+  if (total_ms) *total_ms = h->prof_ms;
+  if (launches) *launches = h->prof_n;
+  return 0;
+}
+extern "C" int smo_kdyn_use_graph(smo_kdyn_t* h, int on) {
+  if (!h) return fail(SMO_E_ARG, "smo_kdyn_use_graph: null handle");
+  h->use_graph = on;
+  return 0;
+}
+
+// host-buffer forms --------------------------------------------------------------------------------------------
+static int kd_reserve_host(smo_kdyn* h, int n_iters) {
+  const size_t vb = sizeof(double) * 3 * h->gsize;
+  if (!h->hB) {
+    TRY(rt_malloc((void**)&h->hB, vb));
+    TRY(rt_malloc((void**)&h->hU, vb));
+    TRY(rt_malloc((void**)&h->hGB, vb));
+    TRY(rt_malloc((void**)&h->hGU, vb));
+  }
+  const size_t need = smo_kdyn_snapshot_bytes(h, n_iters);
+  if (need > h->cap_snap) {
+    rt_free(h->snaps); h->snaps = nullptr; h->cap_snap = 0;
+    TRY(rt_malloc((void**)&h->snaps, need));
+    h->cap_snap = need;
+  }
+  return 0;
+}
+// full host vector [3][M][M][M]  <->  local slab [3][M][M][nz]
+static int kd_slab_copy(smo_kdyn* h, double* dev, const double* host_in, double* host_out, rt_stream st) {
+  const size_t M = h->M, rows = 3 * M * M;
+  if (h->nranks == 1) {
+    if (host_in) return rt_h2d(dev, host_in, sizeof(double) * 3 * h->gsize, st);
+    return rt_d2h(host_out, dev, sizeof(double) * 3 * h->gsize, st);
+  }
+  if (host_in) return rt_copy2d(dev, h->nz * sizeof(double), host_in + h->z0, M * sizeof(double), h->nz * sizeof(double), rows, 0, st);
+  return rt_copy2d(host_out + h->z0, M * sizeof(double), dev, h->nz * sizeof(double), h->nz * sizeof(double), rows, 1, st);
+}
+extern "C" int smo_kdyn_forward_host(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt,
+                                     int n_iters, double* J_host, int flags, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward_host"));
+  if (!B0 || !U || !J_host) return fail(SMO_E_ARG, "smo_kdyn_forward_host: null buffer");
+  rt_stream st = (rt_stream)stream;
+  TRY(kd_reserve_host(h, n_iters));
+  TRY(kd_slab_copy(h, h->hB, B0, nullptr, st));
+  TRY(kd_slab_copy(h, h->hU, U, nullptr, st));
+  return smo_kdyn_forward(h, h->hB, h->hU, Rm, dt, n_iters, h->snaps, J_host, flags, stream);
+}
+extern "C" int smo_kdyn_adjoint_host(smo_kdyn_t* h, double Rm, double dt, int n_iters, double* gB, double* gU,
+                                     int flags, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_adjoint_host"));
+  if (!gB || !gU) return fail(SMO_E_ARG, "smo_kdyn_adjoint_host: null buffer");
+  if (!h->snaps || smo_kdyn_snapshot_bytes(h, n_iters) > h->cap_snap)
+    return fail(SMO_E_STATE, "smo_kdyn_adjoint_host: no matching forward solve on this handle");
+  rt_stream st = (rt_stream)stream;
+  TRY(smo_kdyn_adjoint(h, Rm, dt, n_iters, h->snaps, h->hGB, h->hGU, flags, stream));
+  TRY(kd_slab_copy(h, h->hGB, nullptr, gB, st));
+  TRY(kd_slab_copy(h, h->hGU, nullptr, gU, st));
+  return rt_sync(st);
+}
+
+#if defined(SMO_EMUL)
+// test-only: communicator made of a host callback (tests/emul drives it with torch.distributed gloo)
+extern "C" void* smo_emul_make_comm(smo_emul_a2a_fn fn, void* user) {
+  EmulComm* c = new EmulComm();
+  c->fn = fn; c->user = user;
+  return c;
+}
+#endif

@@ -1,0 +1,112 @@
+// Common definitions for the spheremanopt_b200 CUDA library (sm_100a, fp64).
+//
+// Kernel bodies are written as a fixed sequence of *phases* separated by CTA-wide barriers:
+//
+//     struct K { struct Params; struct State; static constexpr int THREADS, NPHASES, MIN_BLOCKS;
+//                template <int PH> SMO_HD static void phase(const Params&, int work, int tid,
+//                                                           unsigned char* smem, State&); };
+//
+// On the device, smo_kernel<K> runs the phases of one work item (tile) per loop trip with
+// __syncthreads() between them; State lives in registers.  With -DSMO_EMUL the very same phase
+// bodies are compiled by g++ and run thread-by-thread on the host (tests/emul): that build is test
+// infrastructure for checking index logic without a GPU and is never loaded by the product package.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+
+#if defined(SMO_EMUL)
+#define SMO_HD inline
+#define SMO_DEV inline
+#include <vector>
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+#else
+#include <cuda_runtime.h>
+#define SMO_HD __host__ __device__ __forceinline__
+#define SMO_DEV __device__ __forceinline__
+#endif
+
+namespace smo {
+
+typedef double2 cplx;   // interleaved (re, im)
+
+constexpr int MAXF = 6;  // max fields handled by one launch
+
+template <class T> SMO_HD T ldg(const T* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+SMO_HD cplx ldg_c(const cplx* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+SMO_HD int imax(int a, int b) { return a > b ? a : b; }
+SMO_HD int imin(int a, int b) { return a < b ? a : b; }
+
+// ---------------------------------------------------------------------------------------------
+// phase runner
+// ---------------------------------------------------------------------------------------------
+// A kernel class K provides
+//   struct Params { int nwork; int nsteps; ... };   struct State { ... };
+//   static constexpr int THREADS, NPHASES, MIN_BLOCKS;
+//   template <int PH> SMO_HD static void phase(const Params&, int work, int step, int tid, unsigned char* smem, State&);
+// For every work item the runner executes  for step in [0,nsteps): phase<0>, sync, phase<1>, sync, ...
+#if !defined(SMO_EMUL)
+template <class K, int PH, bool END> struct PhaseStep;
+template <class K, int PH> struct PhaseStep<K, PH, false> {
+  static __device__ __forceinline__ void run(const typename K::Params& p, int work, int step, int tid,
+                                             unsigned char* smem, typename K::State& st) {
+    K::template phase<PH>(p, work, step, tid, smem, st);
+    __syncthreads();
+    PhaseStep<K, PH + 1, (PH + 1 >= K::NPHASES)>::run(p, work, step, tid, smem, st);
+  }
+};
+template <class K, int PH> struct PhaseStep<K, PH, true> {
+  static __device__ __forceinline__ void run(const typename K::Params&, int, int, int, unsigned char*,
+                                             typename K::State&) {}
+};
+
+// One CTA loops over work items blockIdx.x, blockIdx.x + gridDim.x, ... (persistent-style grid).
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const typename K::Params p) {
+  extern __shared__ __align__(16) unsigned char smo_smem[];
+  typename K::State st;
+  for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+    for (int step = 0; step < p.nsteps; ++step)
+      PhaseStep<K, 0, false>::run(p, work, step, (int)threadIdx.x, smo_smem, st);
+  }
+}
+#else
+template <class K, int PH, bool END> struct EmulStep;
+template <class K, int PH> struct EmulStep<K, PH, false> {
+  static void run(const typename K::Params& p, int work, int step, unsigned char* smem,
+                  std::vector<typename K::State>& st) {
+    for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<PH>(p, work, step, tid, smem, st[tid]);
+    EmulStep<K, PH + 1, (PH + 1 >= K::NPHASES)>::run(p, work, step, smem, st);
+  }
+};
+template <class K, int PH> struct EmulStep<K, PH, true> {
+  static void run(const typename K::Params&, int, int, unsigned char*, std::vector<typename K::State>&) {}
+};
+// Host emulation of smo_kernel<K>: CTAs run one after another, threads of a CTA phase by phase.
+template <class K> void emul_kernel(int grid, size_t smem_bytes, const typename K::Params& p) {
+  std::vector<unsigned char> smem(smem_bytes + 64);
+  unsigned char* sm = smem.data();
+  sm += (16 - ((uintptr_t)sm & 15)) & 15;
+  std::vector<typename K::State> st(K::THREADS);
+  for (int cta = 0; cta < grid; ++cta)
+    for (int work = cta; work < p.nwork; work += grid)
+      for (int step = 0; step < p.nsteps; ++step) EmulStep<K, 0, false>::run(p, work, step, sm, st);
+}
+#endif
+
+}  // namespace smo
