@@ -54,14 +54,19 @@ int smo_sh23_adjoint(smo_sh23_t* h, int batch, double dt, int n_iters, const voi
 /* Replaces FWD_Solve_IVP_PREP (SH:334-407): n_iters+1 SBDF1 steps, final state on the grid -> out_dev [batch][M]. */
 int smo_sh23_prep(smo_sh23_t* h, const double* X_dev, int batch, double dt, int n_iters, double* out_dev,
                   void* stream);
-/* Host-buffer forms of the three calls above (copies inside, synchronous on return): the drop-in for the
- * reference's numpy-in / numpy-out callables.  The snapshot store stays on the device inside the handle. */
-int smo_sh23_forward_host(smo_sh23_t* h, const double* X_host, int batch, double dt, int n_iters, double* J_host,
-                          void* stream);
-int smo_sh23_adjoint_host(smo_sh23_t* h, int batch, double dt, int n_iters, double* grad_host, int flags,
-                          void* stream);
-/* copy the handle-owned snapshot store of the last *_host forward to the host ([batch][n_iters+1][Npts/2] complex128) */
-int smo_sh23_snapshots_to_host(smo_sh23_t* h, int batch, int n_iters, void* snaps_host, void* stream);
+/* transform helpers (initial conditions, tests): grid [batch][M] <-> retained coefficients [batch][Npts/2] complex128,
+ * Dedalus conventions ([D2-1..3]): coefficients are amplitudes, scale change = zero-pad / truncate */
+int smo_sh23_to_coef(smo_sh23_t* h, const double* X_dev, int batch, void* coef_dev, void* stream);
+int smo_sh23_to_grid(smo_sh23_t* h, const void* coef_dev, int batch, double* out_dev, void* stream);
+/* Host-buffer forms of the calls above (copies inside, synchronous on return): the drop-in for the reference's
+ * numpy-in / numpy-out callables.  The snapshot store stays on the device: snaps_dev as above, or NULL to use a
+ * store owned by the handle (grown on demand). */
+int smo_sh23_forward_host(smo_sh23_t* h, const double* X_host, int batch, double dt, int n_iters, void* snaps_dev,
+                          double* J_host, void* stream);
+int smo_sh23_adjoint_host(smo_sh23_t* h, int batch, double dt, int n_iters, const void* snaps_dev, double* grad_host,
+                          int flags, void* stream);
+int smo_sh23_prep_host(smo_sh23_t* h, const double* X_host, int batch, double dt, int n_iters, double* out_host,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Kinematic dynamo (3-D periodic Fourier, CNAB1, dealias 3/2), slab-decomposed over nranks GPUs
@@ -89,12 +94,15 @@ int smo_kdyn_adjoint(smo_kdyn_t* h, double Rm, double dt, int n_iters, const voi
  * the grid -> out_dev [3][grid_elems]. */
 int smo_kdyn_prep(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, double Rm, double dt, int n_iters,
                   double* out_dev, void* stream);
-/* Host-buffer forms: full-size reference vectors (3*M^3 doubles) on the host; each rank reads/writes its z-slab.
- * The snapshot store is owned by the handle.  Synchronous on return. */
+/* Host-buffer forms: full-size reference vectors (3*M^3 doubles) on the host; each rank reads/writes its z-slab
+ * (the other entries of the gradient outputs are left untouched).  snaps_dev as above, or NULL to use a store owned
+ * by the handle.  Synchronous on return. */
 int smo_kdyn_forward_host(smo_kdyn_t* h, const double* B0_host, const double* U_host, double Rm, double dt,
-                          int n_iters, double* J_host, int flags, void* stream);
-int smo_kdyn_adjoint_host(smo_kdyn_t* h, double Rm, double dt, int n_iters, double* gradB_host, double* gradU_host,
-                          int flags, void* stream);
+                          int n_iters, void* snaps_dev, double* J_host, int flags, void* stream);
+int smo_kdyn_adjoint_host(smo_kdyn_t* h, double Rm, double dt, int n_iters, const void* snaps_dev, double* gradB_host,
+                          double* gradU_host, int flags, void* stream);
+int smo_kdyn_prep_host(smo_kdyn_t* h, const double* B0_host, const double* U_host, double Rm, double dt, int n_iters,
+                       double* out_host, void* stream);
 /* transform helpers (tests, initial conditions): grid [3][grid_elems] <-> coefficients [3][coef_elems] */
 int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid_dev, void* coef_dev, void* stream);
 int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef_dev, double* grid_dev, void* stream);
@@ -104,6 +112,17 @@ int smo_kdyn_profile_set(smo_kdyn_t* h, int which);
 int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long* launches);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Communicator for the slab-decomposed dynamo (replaces the MPI communicator Dedalus uses for its layout
+ * transposes, [D2-9]; FWD_Solve_KDyn.py:3 `from mpi4py import MPI`).  One process per GPU: rank 0 calls
+ * smo_comm_get_unique_id, the bytes are broadcast by the host program (e.g. torch.distributed), every rank calls
+ * smo_comm_create and passes the result as nccl_comm to smo_kdyn_create.
+ * ---------------------------------------------------------------------------------------------------------- */
+int smo_comm_unique_id_bytes(void);
+int smo_comm_get_unique_id(void* id_out);
+int smo_comm_create(void** comm, const void* id, int nranks, int rank);
+int smo_comm_destroy(void* comm);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Inner product and sphere geometry on device vectors (rows A5/B5 and C1-C3)

@@ -31,7 +31,8 @@ struct Sh23Params {
   int nwork, nsteps;
   int batch, n_iters, Nh;
   double dt, a, kfac;    // kfac = 2 pi / L
-  int flags;             // bit0: continuous adjoint; bit1: prep mode
+  int flags;             // bit0: continuous adjoint; bit1: prep mode; bit2: initial state given as coefficients
+  const cplx* cin;       // [batch][Nh] initial coefficients (bit2)
   const cplx* twH;       // exp(-2 pi i m / H)
   const cplx* twM;       // exp(-2 pi i m / M)
 };
@@ -164,7 +165,7 @@ template <class F, int NI_> struct Sh23Fwd {
           for (int i = 0; i < R2; ++i) {
             const int nn = jj + R1 * i;
             double a0 = 0.0, a1 = 0.0;
-            if (live) { a0 = p.X[(long long)inst * M + 2 * nn]; a1 = p.X[(long long)inst * M + 2 * nn + 1]; }
+            if (live && !(p.flags & 4)) { a0 = p.X[(long long)inst * M + 2 * nn]; a1 = p.X[(long long)inst * M + 2 * nn + 1]; }
             st.re[i] = a0; st.im[i] = a1;
           }
         }
@@ -205,7 +206,11 @@ template <class F, int NI_> struct Sh23Fwd {
       }
     } else {
       if (step == 0) {
-        for (int k = jj; k < Nh; k += RT) C[k] = Cr::postprocess(p, XA, k);
+        if (p.flags & 4) {
+          for (int k = jj; k < Nh; k += RT) C[k] = live ? p.cin[(long long)inst * Nh + k] : make_double2(0.0, 0.0);
+        } else {
+          for (int k = jj; k < Nh; k += RT) C[k] = Cr::postprocess(p, XA, k);
+        }
       } else if (do_upd) {
         for (int k = jj; k < Nh; k += RT) {
           const cplx nh = Cr::postprocess(p, XA, k);

@@ -21,6 +21,43 @@
 
 #if !defined(SMO_EMUL) && defined(SMO_WITH_NCCL)
 #include <nccl.h>
+#include <dlfcn.h>
+// NCCL is bound at run time (dlopen) so that the library shares whatever libnccl.so.2 the host program (e.g.
+// PyTorch) has already loaded instead of pulling in a second copy at link time.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    api.ok = false;
+    void* so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (so) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(so, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(so, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(so, "ncclCommDestroy");
+      api.GroupStart = (decltype(api.GroupStart))dlsym(so, "ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))dlsym(so, "ncclGroupEnd");
+      api.Send = (decltype(api.Send))dlsym(so, "ncclSend");
+      api.Recv = (decltype(api.Recv))dlsym(so, "ncclRecv");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(so, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
+               api.Recv && api.GetErrorString;
+    }
+  }
+  return api.ok ? &api : nullptr;
+}
 #endif
 
 using namespace smo;
@@ -292,6 +329,23 @@ extern "C" int smo_sh23_prep(smo_sh23_t* h, const double* X, int batch, double d
   p.nsteps = n_iters + 3;
   return sh23_dispatch(h, false, p, (rt_stream)stream);
 }
+static int sh23_reserve(smo_sh23* h, int batch, int n_iters);
+extern "C" int smo_sh23_to_coef(smo_sh23_t* h, const double* X, int batch, void* coef, void* stream) {
+  TRY(sh23_args(h, batch, 1.0, 0, "smo_sh23_to_coef"));
+  if (!X || !coef) return fail(SMO_E_ARG, "smo_sh23_to_coef: null buffer");
+  TRY(sh23_reserve(h, batch, -1));
+  // a forward solve of zero steps stores snapshot 0 = trunc(FFT(X))/M
+  return smo_sh23_forward(h, X, batch, 1.0, 0, coef, h->jout, stream);
+}
+extern "C" int smo_sh23_to_grid(smo_sh23_t* h, const void* coef, int batch, double* out, void* stream) {
+  TRY(sh23_args(h, batch, 1.0, 0, "smo_sh23_to_grid"));
+  if (!out || !coef) return fail(SMO_E_ARG, "smo_sh23_to_grid: null buffer");
+  Sh23Params p;
+  memset(&p, 0, sizeof p);
+  p.cin = (const cplx*)coef; p.grad = out; p.batch = batch; p.n_iters = -1; p.dt = 1.0; p.flags = 2 | 4;
+  p.nsteps = 2;   // step 0 loads the coefficients, step 1 = final inverse transform of prep mode
+  return sh23_dispatch(h, false, p, (rt_stream)stream);
+}
 extern "C" int smo_sh23_adjoint(smo_sh23_t* h, int batch, double dt, int n_iters, const void* snaps, double* grad,
                                 int flags, void* stream) {
   TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_adjoint"));
@@ -312,7 +366,7 @@ static int sh23_reserve(smo_sh23* h, int batch, int n_iters) {
     TRY(rt_malloc((void**)&h->jout, sizeof(double) * batch));
     h->cap_batch = batch;
   }
-  const size_t need = smo_sh23_snapshot_bytes(h, n_iters) * batch;
+  const size_t need = n_iters < 0 ? 0 : smo_sh23_snapshot_bytes(h, n_iters) * batch;   // n_iters < 0: caller's store
   if (need > h->cap_snap) {
     rt_free(h->snaps); h->snaps = nullptr; h->cap_snap = 0;
     TRY(rt_malloc((void**)&h->snaps, need));
@@ -320,32 +374,38 @@ static int sh23_reserve(smo_sh23* h, int batch, int n_iters) {
   }
   return 0;
 }
-extern "C" int smo_sh23_forward_host(smo_sh23_t* h, const double* X, int batch, double dt, int n_iters, double* J,
-                                     void* stream) {
+extern "C" int smo_sh23_forward_host(smo_sh23_t* h, const double* X, int batch, double dt, int n_iters, void* snaps,
+                                     double* J, void* stream) {
   TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_forward_host"));
   if (!X || !J) return fail(SMO_E_ARG, "smo_sh23_forward_host: null buffer");
   rt_stream st = (rt_stream)stream;
-  TRY(sh23_reserve(h, batch, n_iters));
+  TRY(sh23_reserve(h, batch, snaps ? -1 : n_iters));
   TRY(rt_h2d(h->xin, X, sizeof(double) * batch * h->M, st));
-  TRY(smo_sh23_forward(h, h->xin, batch, dt, n_iters, h->snaps, h->jout, stream));
+  TRY(smo_sh23_forward(h, h->xin, batch, dt, n_iters, snaps ? snaps : h->snaps, h->jout, stream));
   TRY(rt_d2h(J, h->jout, sizeof(double) * batch, st));
   return rt_sync(st);
 }
-extern "C" int smo_sh23_adjoint_host(smo_sh23_t* h, int batch, double dt, int n_iters, double* grad, int flags,
-                                     void* stream) {
+extern "C" int smo_sh23_adjoint_host(smo_sh23_t* h, int batch, double dt, int n_iters, const void* snaps, double* grad,
+                                     int flags, void* stream) {
   TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_adjoint_host"));
   if (!grad) return fail(SMO_E_ARG, "smo_sh23_adjoint_host: null buffer");
-  if (!h->snaps || (size_t)batch > h->cap_batch || smo_sh23_snapshot_bytes(h, n_iters) * batch > h->cap_snap)
+  if (!snaps && (!h->snaps || smo_sh23_snapshot_bytes(h, n_iters) * batch > h->cap_snap))
     return fail(SMO_E_STATE, "smo_sh23_adjoint_host: no matching forward solve on this handle");
   rt_stream st = (rt_stream)stream;
-  TRY(smo_sh23_adjoint(h, batch, dt, n_iters, h->snaps, h->gout, flags, stream));
+  TRY(sh23_reserve(h, batch, -1));
+  TRY(smo_sh23_adjoint(h, batch, dt, n_iters, snaps ? snaps : h->snaps, h->gout, flags, stream));
   TRY(rt_d2h(grad, h->gout, sizeof(double) * batch * h->M, st));
   return rt_sync(st);
 }
-extern "C" int smo_sh23_snapshots_to_host(smo_sh23_t* h, int batch, int n_iters, void* out, void* stream) {
-  if (!h || !out || !h->snaps) return fail(SMO_E_STATE, "smo_sh23_snapshots_to_host: no snapshots");
+extern "C" int smo_sh23_prep_host(smo_sh23_t* h, const double* X, int batch, double dt, int n_iters, double* out,
+                                  void* stream) {
+  TRY(sh23_args(h, batch, dt, n_iters, "smo_sh23_prep_host"));
+  if (!X || !out) return fail(SMO_E_ARG, "smo_sh23_prep_host: null buffer");
   rt_stream st = (rt_stream)stream;
-  TRY(rt_d2h(out, h->snaps, smo_sh23_snapshot_bytes(h, n_iters) * batch, st));
+  TRY(sh23_reserve(h, batch, -1));
+  TRY(rt_h2d(h->xin, X, sizeof(double) * batch * h->M, st));
+  TRY(smo_sh23_prep(h, h->xin, batch, dt, n_iters, h->gout, stream));
+  TRY(rt_d2h(out, h->gout, sizeof(double) * batch * h->M, st));
   return rt_sync(st);
 }
 
@@ -425,16 +485,18 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
   return 0;
 #elif defined(SMO_WITH_NCCL)
   ncclComm_t comm = (ncclComm_t)h->comm;
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(SMO_E_COMM, "libnccl.so.2 could not be loaded");
   prof_begin(h, PK_A2A, st);
-  if (ncclGroupStart() != ncclSuccess) return fail(SMO_E_COMM, "ncclGroupStart failed");
+  if (nc->GroupStart() != ncclSuccess) return fail(SMO_E_COMM, "ncclGroupStart failed");
   for (int f = 0; f < nf; ++f)
     for (int s = 0; s < h->nranks; ++s) {
-      ncclResult_t r1 = ncclSend(src[f] + blk * s, blk * 2, ncclDouble, s, comm, st);
-      ncclResult_t r2 = ncclRecv(dst[f] + blk * s, blk * 2, ncclDouble, s, comm, st);
-      if (r1 != ncclSuccess || r2 != ncclSuccess) { ncclGroupEnd(); return fail(SMO_E_COMM, "ncclSend/Recv failed: %s", ncclGetErrorString(r1 != ncclSuccess ? r1 : r2)); }
+      ncclResult_t r1 = nc->Send(src[f] + blk * s, blk * 2, ncclDouble, s, comm, st);
+      ncclResult_t r2 = nc->Recv(dst[f] + blk * s, blk * 2, ncclDouble, s, comm, st);
+      if (r1 != ncclSuccess || r2 != ncclSuccess) { nc->GroupEnd(); return fail(SMO_E_COMM, "ncclSend/Recv failed: %s", nc->GetErrorString(r1 != ncclSuccess ? r1 : r2)); }
     }
-  ncclResult_t r = ncclGroupEnd();
-  if (r != ncclSuccess) return fail(SMO_E_COMM, "ncclGroupEnd failed: %s", ncclGetErrorString(r));
+  ncclResult_t r = nc->GroupEnd();
+  if (r != ncclSuccess) return fail(SMO_E_COMM, "ncclGroupEnd failed: %s", nc->GetErrorString(r));
   prof_end(h, PK_A2A, st);
   return 0;
 #else
@@ -867,7 +929,7 @@ static int kd_reserve_host(smo_kdyn* h, int n_iters) {
     TRY(rt_malloc((void**)&h->hGB, vb));
     TRY(rt_malloc((void**)&h->hGU, vb));
   }
-  const size_t need = smo_kdyn_snapshot_bytes(h, n_iters);
+  const size_t need = n_iters < 0 ? 0 : smo_kdyn_snapshot_bytes(h, n_iters);   // n_iters < 0: caller's store
   if (need > h->cap_snap) {
     rt_free(h->snaps); h->snaps = nullptr; h->cap_snap = 0;
     TRY(rt_malloc((void**)&h->snaps, need));
@@ -886,27 +948,83 @@ static int kd_slab_copy(smo_kdyn* h, double* dev, const double* host_in, double*
   return rt_copy2d(host_out + h->z0, M * sizeof(double), dev, h->nz * sizeof(double), h->nz * sizeof(double), rows, 1, st);
 }
 extern "C" int smo_kdyn_forward_host(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt,
-                                     int n_iters, double* J_host, int flags, void* stream) {
+                                     int n_iters, void* snaps, double* J_host, int flags, void* stream) {
   TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward_host"));
   if (!B0 || !U || !J_host) return fail(SMO_E_ARG, "smo_kdyn_forward_host: null buffer");
   rt_stream st = (rt_stream)stream;
-  TRY(kd_reserve_host(h, n_iters));
+  TRY(kd_reserve_host(h, snaps ? -1 : n_iters));
   TRY(kd_slab_copy(h, h->hB, B0, nullptr, st));
   TRY(kd_slab_copy(h, h->hU, U, nullptr, st));
-  return smo_kdyn_forward(h, h->hB, h->hU, Rm, dt, n_iters, h->snaps, J_host, flags, stream);
+  return smo_kdyn_forward(h, h->hB, h->hU, Rm, dt, n_iters, snaps ? snaps : h->snaps, J_host, flags, stream);
 }
-extern "C" int smo_kdyn_adjoint_host(smo_kdyn_t* h, double Rm, double dt, int n_iters, double* gB, double* gU,
-                                     int flags, void* stream) {
+extern "C" int smo_kdyn_adjoint_host(smo_kdyn_t* h, double Rm, double dt, int n_iters, const void* snaps, double* gB,
+                                     double* gU, int flags, void* stream) {
   TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_adjoint_host"));
   if (!gB || !gU) return fail(SMO_E_ARG, "smo_kdyn_adjoint_host: null buffer");
-  if (!h->snaps || smo_kdyn_snapshot_bytes(h, n_iters) > h->cap_snap)
+  if (!snaps && (!h->snaps || smo_kdyn_snapshot_bytes(h, n_iters) > h->cap_snap))
     return fail(SMO_E_STATE, "smo_kdyn_adjoint_host: no matching forward solve on this handle");
   rt_stream st = (rt_stream)stream;
-  TRY(smo_kdyn_adjoint(h, Rm, dt, n_iters, h->snaps, h->hGB, h->hGU, flags, stream));
+  TRY(kd_reserve_host(h, -1));
+  TRY(smo_kdyn_adjoint(h, Rm, dt, n_iters, snaps ? snaps : h->snaps, h->hGB, h->hGU, flags, stream));
   TRY(kd_slab_copy(h, h->hGB, nullptr, gB, st));
   TRY(kd_slab_copy(h, h->hGU, nullptr, gU, st));
   return rt_sync(st);
 }
+extern "C" int smo_kdyn_prep_host(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
+                                  double* out, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, 0, "smo_kdyn_prep_host"));
+  if (!B0 || !U || !out) return fail(SMO_E_ARG, "smo_kdyn_prep_host: null buffer");
+  rt_stream st = (rt_stream)stream;
+  TRY(kd_reserve_host(h, -1));
+  TRY(kd_slab_copy(h, h->hB, B0, nullptr, st));
+  TRY(kd_slab_copy(h, h->hU, U, nullptr, st));
+  TRY(smo_kdyn_prep(h, h->hB, h->hU, Rm, dt, n_iters, h->hGB, stream));
+  TRY(kd_slab_copy(h, h->hGB, nullptr, out, st));
+  return rt_sync(st);
+}
+
+// communicator ------------------------------------------------------------------------------------------------
+#if !defined(SMO_EMUL) && defined(SMO_WITH_NCCL)
+extern "C" int smo_comm_unique_id_bytes(void) { return (int)sizeof(ncclUniqueId); }
+extern "C" int smo_comm_get_unique_id(void* id_out) {
+  if (!id_out) return fail(SMO_E_ARG, "smo_comm_get_unique_id: null buffer");
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(SMO_E_COMM, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  ncclResult_t r = nc->GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(SMO_E_COMM, "ncclGetUniqueId failed: %s", nc->GetErrorString(r));
+  memcpy(id_out, &id, sizeof id);
+  return 0;
+}
+extern "C" int smo_comm_create(void** comm, const void* id_in, int nranks, int rank) {
+  if (!comm || !id_in || nranks < 1 || rank < 0 || rank >= nranks) return fail(SMO_E_ARG, "smo_comm_create: bad argument");
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(SMO_E_COMM, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  memcpy(&id, id_in, sizeof id);
+  ncclComm_t c;
+  ncclResult_t r = nc->CommInitRank(&c, nranks, id, rank);
+  if (r != ncclSuccess) return fail(SMO_E_COMM, "ncclCommInitRank failed: %s", nc->GetErrorString(r));
+  *comm = (void*)c;
+  return 0;
+}
+extern "C" int smo_comm_destroy(void* comm) {
+  NcclApi* nc = nccl_api();
+  if (comm && nc) nc->CommDestroy((ncclComm_t)comm);
+  return 0;
+}
+#else
+extern "C" int smo_comm_unique_id_bytes(void) { return 128; }
+extern "C" int smo_comm_get_unique_id(void* id_out) {
+  if (!id_out) return fail(SMO_E_ARG, "smo_comm_get_unique_id: null buffer");
+  memset(id_out, 0, 128);
+  return 0;
+}
+extern "C" int smo_comm_create(void**, const void*, int, int) {
+  return fail(SMO_E_UNSUPPORTED, "library built without NCCL");
+}
+extern "C" int smo_comm_destroy(void*) { return 0; }
+#endif
 
 #if defined(SMO_EMUL)
 // test-only: communicator made of a host callback (tests/emul drives it with torch.distributed gloo)

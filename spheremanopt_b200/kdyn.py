@@ -1,0 +1,305 @@
+"""B200 drop-in for Example_Problems/Periodic_Domain(Fourier)/Kinematic_Dynamo/FWD_Solve_KDyn.py (alias ``KD``).
+
+Same function names, argument order and return conventions as the reference, so that its driver block
+(KD:1025-1067) works unchanged with these callables:
+
+    domain, Bx0, Ux = Generate_IC(Npts, X_domain, M_0, Noise)         # KD:183-317
+    X_FWD_DICT      = GEN_BUFFER(Npts, domain, N_SUB_ITERS)            # KD:319-355
+    args_IP = (domain, None)
+    args_f  = [domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, "Final", "Discrete"]
+    Optimise_On_Multi_Sphere([Bx0, Ux], [M_0, E_0], FWD_Solve_IVP_Lin, ADJ_Solve_IVP_Lin, Inner_Prod_3, args_f, args_IP, ...)
+
+Vectors are float64 numpy arrays ``concat(Fx.ravel(), Fy.ravel(), Fz.ravel())`` on the 3/2-dealiased M^3 grid
+(KD:137; "Mode H", replicated on every rank exactly like the reference's allgather'ed vectors) or ``DevVec`` objects
+holding this rank's z-slab [3][M][M][nz] in HBM ("Mode D").  With more than one rank (one process per GPU,
+torch.distributed initialised) the grid is slab-decomposed: coefficient space along kx, grid space along z, with
+all-to-all transposes inside the library - the replacement of Dedalus' MPI transposes [D2-9].
+All arithmetic happens in libsmo_b200.so; there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .devvec import DevVec, VecOps, _stream_ptr
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class Domain:
+    """Stand-in for the dedalus domain of KD:212-216 (three Fourier bases, Npts modes each, dealias 3/2)."""
+
+    def __init__(self, Npts, X=(0., 2. * np.pi), device=None, distributed=None):
+        self.lib = _cabi.load()
+        self.N = int(Npts)
+        self.dealias = 3 / 2
+        self.M = 3 * self.N // 2
+        self.Nh = self.N // 2
+        self.kmax = (self.N - 1) // 2
+        self.Nc = 2 * self.kmax + 1
+        self.interval = (float(X[0]), float(X[1]))
+        self.L = self.interval[1] - self.interval[0]
+        self.hypervolume = self.L ** 3
+        dist = _dist() if distributed in (None, True) else None
+        self.rank = dist.get_rank() if dist else 0
+        self.nranks = dist.get_world_size() if dist else 1
+        if device is None:
+            device = "cuda:%d" % (self.rank % max(torch.cuda.device_count(), 1))
+        self.device = torch.device(device)
+        self.comm = None
+        with torch.cuda.device(self.device):
+            if self.nranks > 1:
+                nb = self.lib.smo_comm_unique_id_bytes()
+                idbuf = (C.c_ubyte * nb)()
+                if self.rank == 0:
+                    _cabi.check(self.lib, self.lib.smo_comm_get_unique_id(idbuf))
+                t = torch.tensor(list(idbuf), dtype=torch.uint8, device=self.device)
+                dist.broadcast(t, 0)
+                idbuf = (C.c_ubyte * nb)(*t.cpu().tolist())
+                comm = C.c_void_p()
+                _cabi.check(self.lib, self.lib.smo_comm_create(C.byref(comm), idbuf, self.nranks, self.rank))
+                self.comm = comm
+            h = C.c_void_p()
+            _cabi.check(self.lib, self.lib.smo_kdyn_create(C.byref(h), self.N, self.L, self.rank, self.nranks, self.comm))
+        self.h = h
+        self.nz = self.M // self.nranks
+        self.z0 = self.rank * self.nz
+        self.nkx = self.Nh // self.nranks
+        self.gsize = self.lib.smo_kdyn_grid_elems(h)     # M*M*nz
+        self.csize = self.lib.smo_kdyn_coef_elems(h)     # nkx*Nc*(Nc+1)
+        self.vec_len = 3 * self.M ** 3                   # the reference's vector length
+        self._vecops = {}
+
+    def vecops(self, n):
+        if n not in self._vecops:
+            self._vecops[n] = VecOps(n, self.device)
+        return self._vecops[n]
+
+    # host vector <-> local slab -----------------------------------------------------------------------------
+    def slab_from_host(self, x):
+        """full reference vector (3*M^3) -> this rank's device slab [3][M][M][nz]"""
+        M = self.M
+        a = np.asarray(x, dtype=np.float64).reshape(3, M, M, M)
+        if self.nranks > 1:
+            a = np.ascontiguousarray(a[:, :, :, self.z0:self.z0 + self.nz])
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=True).reshape(-1)
+
+    def host_from_slab(self, t):
+        """device slab -> full reference vector on the host (all-gather over ranks, like KD:118-137)"""
+        M = self.M
+        if self.nranks == 1:
+            return t.cpu().numpy()
+        dist = _dist()
+        parts = [torch.empty_like(t) for _ in range(self.nranks)]
+        dist.all_gather(parts, t)
+        full = torch.cat([p.view(3, M, M, self.nz) for p in parts], dim=3)
+        return full.reshape(-1).cpu().numpy()
+
+    def allreduce_sum(self, v):
+        if self.nranks == 1:
+            return v
+        dist = _dist()
+        # gather the per-rank partials and add them in rank order: bit-identical on every rank
+        t = torch.tensor([v], dtype=torch.float64, device=self.device)
+        parts = [torch.empty_like(t) for _ in range(self.nranks)]
+        dist.all_gather(parts, t)
+        s = 0.0
+        for p in torch.cat(parts).cpu().tolist():
+            s += p
+        return s
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.smo_kdyn_destroy(self.h)
+                self.h = None
+            if getattr(self, "comm", None):
+                self.lib.smo_comm_destroy(self.comm)
+                self.comm = None
+        except Exception:
+            pass
+
+
+class SnapshotStore(dict):
+    """Device-resident replacement of ``{'A_fwd','B_fwd','C_fwd'}`` (KD:347-355): [N_SUB_ITERS+1][3][nkx][Nc][Nc+1]
+    complex128 in HBM (this rank's kx-slab).  ``['A_fwd']`` etc. return host copies in the reference's
+    [Npts/2, Npts-1, Npts-1, N_SUB_ITERS+1] orientation (single rank only), for inspection."""
+
+    def __init__(self, domain, n_iters):
+        super().__init__()
+        self.domain, self.n_iters = domain, int(n_iters)
+        nbytes = domain.lib.smo_kdyn_snapshot_bytes(domain.h, self.n_iters)
+        self.buf = torch.zeros(nbytes // 16, dtype=torch.complex128, device=domain.device)
+        self.valid = False
+
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def __getitem__(self, key):
+        c = {'A_fwd': 0, 'B_fwd': 1, 'C_fwd': 2}[key]
+        d = self.domain
+        a = self.buf.view(self.n_iters + 1, 3, d.nkx, d.Nc, d.Nc + 1)[:, c, :, :, :d.Nc]
+        return np.transpose(a.cpu().numpy(), (1, 2, 3, 0)).copy()
+
+
+def GEN_BUFFER(Npts, domain, N_SUB_ITERS):
+    """KD:319-355"""
+    return SnapshotStore(domain, N_SUB_ITERS)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _as_slab(domain, x):
+    if isinstance(x, DevVec):
+        return x.t
+    if isinstance(x, torch.Tensor):
+        return x
+    return domain.slab_from_host(x)
+
+
+def _wrap_like(domain, proto, t):
+    if isinstance(proto, DevVec):
+        return DevVec(t)
+    return domain.host_from_slab(t)
+
+
+def Inner_Prod_3(x, y, domain, random_arg=None):
+    """KD:173-181: (1/V) integ(x.y) dV = (1/M^3) * sum over all 3*M^3 entries of x_j*y_j (raw vectors)."""
+    if isinstance(x, DevVec) or isinstance(y, DevVec) or domain.nranks == 1:
+        xt, yt = _as_slab(domain, x), _as_slab(domain, y)
+        v = domain.vecops(xt.numel()).dot(xt, yt, 1.0 / float(domain.M) ** 3)
+        return domain.allreduce_sum(v)
+    # replicated host vectors on several ranks: every rank reduces its slab, partials added in rank order
+    xt, yt = domain.slab_from_host(x), domain.slab_from_host(y)
+    v = domain.vecops(xt.numel()).dot(xt, yt, 1.0 / float(domain.M) ** 3)
+    return domain.allreduce_sum(v)
+
+
+def _flags(Cost_function, Adjoint_type):
+    f = 0
+    if Cost_function == "Integrated":
+        f |= _cabi.SMO_COST_INTEGRATED
+    elif Cost_function != "Final":
+        raise ValueError(Cost_function)
+    if Adjoint_type == "Continuous":
+        f |= _cabi.SMO_ADJOINT_CONTINUOUS
+    elif Adjoint_type != "Discrete":
+        raise ValueError(Adjoint_type)
+    return f
+
+
+def FWD_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost_function="Final", Adjoint_type="Discrete"):
+    """KD:529-689.  Returns -J, J = <B^N,B^N> ("Final"); fills the snapshot store and caches U for the adjoint."""
+    if N_SUB_ITERS != N_ITERS:
+        raise NotImplementedError("N_SUB_ITERS != N_ITERS (the reference script sets them equal, KD:1031)")
+    if N_ITERS != X_FWD_DICT.n_iters:
+        raise ValueError("snapshot store was allocated for N_ITERS=%d" % X_FWD_DICT.n_iters)
+    Bt, Ut = _as_slab(domain, X0[0]), _as_slab(domain, X0[1])
+    J = C.c_double()
+    with torch.cuda.device(domain.device):
+        _cabi.check(domain.lib, domain.lib.smo_kdyn_forward(domain.h, Bt.data_ptr(), Ut.data_ptr(), float(Rm), float(dt),
+                                                            int(N_ITERS), X_FWD_DICT.ptr(), C.byref(J),
+                                                            _flags(Cost_function, "Discrete"), _stream_ptr()))
+    X_FWD_DICT.valid = True
+    return (-1.) * domain.allreduce_sum(J.value)
+
+
+def ADJ_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost_function="Final", Adjoint_type="Discrete"):
+    """KD:766-1004.  Returns [dJ/dB0, dJ/dU] in the layout/type of X0."""
+    if not X_FWD_DICT.valid:
+        raise RuntimeError("ADJ_Solve_IVP_Lin needs the snapshots of a preceding FWD_Solve_IVP_Lin (KD:955-957)")
+    gB = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
+    gU = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
+    with torch.cuda.device(domain.device):
+        _cabi.check(domain.lib, domain.lib.smo_kdyn_adjoint(domain.h, float(Rm), float(dt), int(N_ITERS), X_FWD_DICT.ptr(),
+                                                            gB.data_ptr(), gU.data_ptr(),
+                                                            _flags(Cost_function, Adjoint_type), _stream_ptr()))
+    return [_wrap_like(domain, X0[0], gB), _wrap_like(domain, X0[1], gU)]
+
+
+def FWD_Solve_IVP_Prep(Bx0, Ux0, domain, Rm, dt, N_ITERS):
+    """KD:452-527: N_ITERS+1 CNAB1 steps; returns the final field on the grid as a device slab [3][M][M][nz]."""
+    Bt, Ut = _as_slab(domain, Bx0), _as_slab(domain, Ux0)
+    out = torch.empty_like(Bt)
+    with torch.cuda.device(domain.device):
+        _cabi.check(domain.lib, domain.lib.smo_kdyn_prep(domain.h, Bt.data_ptr(), Ut.data_ptr(), float(Rm), float(dt),
+                                                         int(N_ITERS), out.data_ptr(), _stream_ptr()))
+    return out
+
+
+def to_coef(domain, g):
+    """grid slab [3][M][M][nz] -> coefficients [3][nkx][Nc][Nc+1] complex128 (last column is padding)"""
+    gt = _as_slab(domain, g)
+    c = torch.zeros(3 * domain.csize, dtype=torch.complex128, device=domain.device)
+    with torch.cuda.device(domain.device):
+        _cabi.check(domain.lib, domain.lib.smo_kdyn_to_coef(domain.h, gt.data_ptr(), c.data_ptr(), _stream_ptr()))
+    return c.view(3, domain.nkx, domain.Nc, domain.Nc + 1)
+
+
+def to_grid(domain, c):
+    g = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
+    with torch.cuda.device(domain.device):
+        _cabi.check(domain.lib, domain.lib.smo_kdyn_to_grid(domain.h, c.contiguous().data_ptr(), g.data_ptr(), _stream_ptr()))
+    return g
+
+
+def _wavenumbers(domain):
+    kf = 2.0 * np.pi / domain.L
+    kx = kf * torch.arange(domain.rank * domain.nkx, (domain.rank + 1) * domain.nkx, dtype=torch.float64, device=domain.device)
+    n = np.concatenate([np.arange(0, domain.kmax + 1), np.arange(-domain.kmax, 0), [0]])   # + padding column
+    kc = kf * torch.from_numpy(n.astype(np.float64)).to(domain.device)
+    return kx.view(-1, 1, 1), kc[:domain.Nc].view(1, -1, 1), kc.view(1, 1, -1)
+
+
+def Generate_IC(Npts, X=(0., 2. * np.pi), M_0=1.0, U_Noise=False, Rm=1.0, dt=5e-04, device=None, as_devvec=False, seeds=(42, 42)):
+    """KD:183-317.  ``Rm``/``dt`` stand for the module-level globals the reference's smoothing step uses instead of
+    Rm_IC/dt_IC (KD:299-302 quirk); defaults are the literals at KD:1028-1029.  ``seeds`` = (B, U) noise seeds; the
+    reference uses 42 for both (KD:224, 272)."""
+    domain = Domain(Npts, X, device)
+    M = domain.M
+    kx, ky, kz = _wavenumbers(domain)
+
+    def filt_mask():
+        # KD:30-55: index/size > 0.25 on ANY axis of the (N/2, N-1, N-1) array is zeroed (index based)
+        ix = torch.from_numpy(np.linspace(0, 1, domain.Nh, endpoint=False)[domain.rank * domain.nkx:(domain.rank + 1) * domain.nkx] <= 0.25)
+        ic = np.linspace(0, 1, domain.Nc, endpoint=False) <= 0.25
+        iy = torch.from_numpy(ic)
+        iz = torch.from_numpy(np.concatenate([ic, [False]]))
+        return (ix.view(-1, 1, 1) & iy.view(1, -1, 1) & iz.view(1, 1, -1)).to(domain.device)
+
+    def curl_of_noise(seed):
+        rand = np.random.RandomState(seed=seed)
+        noise = rand.standard_normal((M, M, M))
+        z = np.zeros_like(noise)
+        phi = to_coef(domain, np.concatenate([noise.ravel(), z.ravel(), z.ravel()]))[0] * filt_mask()
+        grads = torch.stack([1j * kx * phi, 1j * ky * phi, 1j * kz * phi])
+        g = to_grid(domain, grads).view(3, -1)
+        px, py, pz = g[0], g[1], g[2]
+        return torch.cat([py - pz, pz - px, px - py])                     # KD:241-243
+
+    B = curl_of_noise(seeds[0])
+    if U_Noise is False:
+        g = domain.interval[0] + domain.L * np.arange(M) / M
+        x = g[:, None, None]; y = g[None, :, None]; z = g[None, None, domain.z0:domain.z0 + domain.nz]
+        one = np.ones((M, M, domain.nz))
+        U = np.concatenate([(0.5 * np.sin(y) * np.cos(z) / np.sqrt(3.) * one).ravel(),     # KD:258-260
+                            (0.5 * np.sin(z) * np.cos(x) / np.sqrt(3.) * one).ravel(),
+                            (0.5 * np.sin(x) * np.cos(y) / np.sqrt(3.) * one).ravel()])
+        U = torch.from_numpy(U).to(domain.device)
+    else:
+        U = curl_of_noise(seeds[1])
+    ip = lambda a: Inner_Prod_3(DevVec(a), DevVec(a), domain)
+    U = U * np.sqrt(1. / ip(U))                                             # KD:287-292
+    B = FWD_Solve_IVP_Prep(B, U, domain, Rm, dt, 100)                       # KD:296-302
+    B = B * np.sqrt(M_0 / ip(B))                                            # KD:305-310
+    if as_devvec:
+        return domain, DevVec(B), DevVec(U)
+    return domain, domain.host_from_slab(B), domain.host_from_slab(U)
+
+
+def File_Manips(k):
+    """KD:1006-1021 copies dedalus HDF5 outputs that this implementation does not write (out of scope)."""
+    return None

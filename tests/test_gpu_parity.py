@@ -1,0 +1,152 @@
+"""GPU parity: the CUDA path, called through the reference-facing callables (which go through the C ABI of
+libsmo_b200.so), against the numpy oracle on the same seeded inputs.  Tolerance: 1e-9 relative (BASELINE north_star)."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import kdyn as okd
+from oracle import sh23 as osh
+from oracle import sphere as osp
+from tests.common import kdyn_field, relerr, sh23_input
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("Npts,dt,nit", [(64, 0.1, 30), (128, 0.05, 40), (256, 0.1, 500)])
+@pytest.mark.parametrize("adj", ["Discrete", "Continuous"])
+def test_sh23_f_gradf(Npts, dt, nit, adj):
+    from spheremanopt_b200 import sh23
+    dom = sh23.Domain(Npts)
+    od = osh.domain_sh23(Npts)
+    X = sh23_input(od, seed=Npts)
+    store = sh23.GEN_BUFFER(dom, nit)
+    f = sh23.FWD_Solve_IVP_Lin([X], dom, dt, nit, nit, store, None, adj)
+    g = sh23.ADJ_Solve_IVP_Lin([X], dom, dt, nit, nit, store, None, adj)
+    D = osh.GEN_BUFFER(od, nit)
+    fo = osh.FWD_Solve_IVP_Lin([X], od, dt, nit, nit, D, None, adj)
+    go = osh.ADJ_Solve_IVP_Lin([X], od, dt, nit, nit, D, None, adj)
+    assert abs(f - fo) <= TOL * abs(fo)
+    assert relerr(store['A_fwd'], D['A_fwd']) <= TOL
+    assert relerr(g[0], go[0]) <= TOL
+    assert abs(sh23.Inner_Prod(X, g[0], dom) - osh.Inner_Prod(X, go[0], od)) <= TOL * abs(osh.Inner_Prod(X, go[0], od))
+
+
+def test_sh23_batch_ragged():
+    """batch sizes that do not fill the last CTA (4 instances per CTA) and more CTAs than one wave"""
+    from spheremanopt_b200 import sh23
+    dom = sh23.Domain(256)
+    od = osh.domain_sh23(256)
+    for batch in (1, 3, 7, 1201):
+        X = np.concatenate([sh23_input(od, seed=b % 5, amp=0.03 + 0.001 * (b % 11)) for b in range(batch)])
+        store = sh23.GEN_BUFFER(dom, 20, batch=batch)
+        J = sh23.forward_batch(X, dom, 0.1, 20, store).cpu().numpy()
+        G = sh23.adjoint_batch(dom, 0.1, 20, store).cpu().numpy().reshape(batch, -1)
+        for b in sorted(set([0, batch // 2, batch - 1])):
+            D = osh.GEN_BUFFER(od, 20)
+            xb = X[b * od.M:(b + 1) * od.M]
+            fo = osh.FWD_Solve_IVP_Lin([xb], od, 0.1, 20, 20, D)
+            go = osh.ADJ_Solve_IVP_Lin([xb], od, 0.1, 20, 20, D)[0]
+            assert abs(-J[b] - fo) <= TOL * abs(fo)
+            assert relerr(G[b], go) <= TOL
+
+
+def test_sh23_generate_ic():
+    from spheremanopt_b200 import sh23
+    dom, X0 = sh23.Generate_IC(0.0725)
+    od, X0o = osh.Generate_IC(0.0725)
+    assert relerr(X0, X0o) <= TOL
+    assert abs(sh23.Inner_Prod(X0, X0, dom) - 0.0725) <= 1e-12
+
+
+@pytest.mark.parametrize("Npts,nit", [(16, 6), (24, 25), (32, 5), (64, 3)])
+def test_kdyn_f_gradf(Npts, nit):
+    from spheremanopt_b200 import kdyn
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    B0 = kdyn_field(od, 1)
+    U = kdyn_field(od, 2)
+    Rm, dt = 1.0, 1e-3
+    store = kdyn.GEN_BUFFER(Npts, dom, nit)
+    f = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, store)
+    g = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, store)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    assert abs(f - fo) <= TOL * abs(fo)
+    for key in ('A_fwd', 'B_fwd', 'C_fwd'):
+        assert relerr(store[key], D[key]) <= TOL
+    assert relerr(g[0], go[0]) <= TOL
+    assert relerr(g[1], go[1]) <= TOL
+    ip, ipo = kdyn.Inner_Prod_3(B0, g[0], dom), okd.Inner_Prod_3(B0, go[0], od)
+    assert abs(ip - ipo) <= TOL * abs(ipo)
+
+
+def test_kdyn_non_solenoidal_input():
+    """adversarial input (not band-limited, not divergence free, non-zero mean): exercises the truncation on first
+    gather, the projection of the parameter field U [D2-8] and the k.B carry of the closed-form CNAB1 pencil"""
+    from spheremanopt_b200 import kdyn
+    Npts, nit = 16, 4
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    r = np.random.RandomState(7)
+    B0 = r.standard_normal(od.vec_len * 3)
+    U = r.standard_normal(od.vec_len * 3)
+    store = kdyn.GEN_BUFFER(Npts, dom, nit)
+    f = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, 2.0, 1e-3, nit, nit, store)
+    g = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, 2.0, 1e-3, nit, nit, store)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D)
+    assert abs(f - fo) <= TOL * abs(fo)
+    assert relerr(g[0], go[0]) <= TOL
+    assert relerr(g[1], go[1]) <= TOL
+
+
+def test_kdyn_generate_ic():
+    from spheremanopt_b200 import kdyn
+    dom, B, U = kdyn.Generate_IC(24, (0., 2. * np.pi), 1.0, True)
+    od, Bo, Uo = okd.Generate_IC(24, (0., 2. * np.pi), 1.0, True)
+    assert relerr(U, Uo) <= TOL
+    assert relerr(B, Bo) <= TOL
+
+
+def test_devvec_and_sphere_ops():
+    import torch
+    from spheremanopt_b200 import kdyn
+    from spheremanopt_b200.devvec import DevVec
+    dom = kdyn.Domain(16)
+    od = okd.domain_kdyn(16)
+    r = np.random.RandomState(0)
+    x, d = r.standard_normal(3 * od.vec_len), r.standard_normal(3 * od.vec_len)
+    X, Dv = DevVec.from_numpy(x), DevVec.from_numpy(d)
+    ipo = lambda a, b: okd.Inner_Prod_3(a, b, od)
+    ip = lambda a, b: kdyn.Inner_Prod_3(a, b, dom)
+    assert abs(ip(X, Dv) - ipo(x, d)) <= 1e-12 * abs(ipo(x, x))
+    # the optimiser's algebra on opaque device vectors
+    y = (np.float64(0.3) * X + Dv * 2.0 - X) .numpy()
+    assert relerr(y, 0.3 * x + d * 2.0 - x) <= 1e-15
+    assert relerr((-X).numpy(), -x) == 0.0
+    c = copy.deepcopy(X)
+    assert c.t.data_ptr() != X.t.data_ptr() and relerr(c.numpy(), x) == 0.0
+    arr = np.atleast_1d([X, Dv])
+    assert arr.dtype == object and arr.shape == (2,)
+    ops = dom.vecops(X.n)
+    scale = 1.0 / od.M ** 3
+    t = ops.project(X.t, Dv.t).cpu().numpy()
+    assert relerr(t, osp.tangent_vector(x, d, okd.Inner_Prod_3, (od,))) <= 1e-13
+    u = ops.retract(X.t, 0.7, Dv.t, 2.5, scale).cpu().numpy()
+    assert relerr(u, osp.Update_vector(x, 0.7, d, 2.5, okd.Inner_Prod_3, (od,))) <= 1e-13
+
+
+def test_errors_are_loud():
+    from spheremanopt_b200 import kdyn, sh23
+    with pytest.raises(RuntimeError):
+        sh23.Domain(100)          # unsupported size -> error code -> RuntimeError with the library's message
+    with pytest.raises(RuntimeError):
+        kdyn.Domain(20)
+    dom = sh23.Domain(64)
+    store = sh23.GEN_BUFFER(dom, 5)
+    with pytest.raises(RuntimeError):
+        sh23.ADJ_Solve_IVP_Lin([np.zeros(128)], dom, 0.1, 5, 5, store)   # Grad_f before f
