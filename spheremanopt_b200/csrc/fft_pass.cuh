@@ -15,6 +15,11 @@
 #pragma once
 #include "fft_core.cuh"
 
+// tuning knobs (overridable with -D for experiments; defaults are the measured best on B200)
+#ifndef SMO_PASS_MB
+#define SMO_PASS_MB 4   // resident CTAs per SM the register allocation of the c2c passes is bounded for
+#endif
+
 namespace smo {
 
 struct PassParams {
@@ -38,7 +43,7 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
   static constexpr int T = T_;
   static constexpr int THREADS = T_ * F::RT;
   static constexpr int NPHASES = 2;
-  static constexpr int MIN_BLOCKS = 1;
+  static constexpr int MIN_BLOCKS = SMO_PASS_MB;
   static constexpr size_t SMEM = (size_t)T_ * F::XP * sizeof(cplx);
   struct State {
     double re[F::RT], im[F::RT];

@@ -505,13 +505,25 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 #endif
 }
 
+#ifndef SMO_TZ
+#define SMO_TZ 8
+#endif
+#ifndef SMO_TY
+#define SMO_TY 8
+#endif
+#ifndef SMO_TX
+#define SMO_TX 8
+#endif
+#ifndef SMO_TXA
+#define SMO_TXA 4
+#endif
 // ---- pass launchers ---------------------------------------------------------------------------------------
 template <int M> struct KdOps {
   typedef typename FacOf<M>::type F;
-  static constexpr int TZ = 8;    // lines per CTA, contiguous (z) passes
-  static constexpr int TY = 8;    // lines per CTA, strided (y) passes
-  static constexpr int TX = 8;    // columns per CTA, x passes with <= 3 fields
-  static constexpr int TXA = 4;   // columns per CTA, fused adjoint x pass (6 fields)
+  static constexpr int TZ = SMO_TZ;    // lines per CTA, contiguous (z) passes
+  static constexpr int TY = SMO_TY;    // lines per CTA, strided (y) passes
+  static constexpr int TX = SMO_TX;    // columns per CTA, x passes with <= 3 fields
+  static constexpr int TXA = SMO_TXA;  // columns per CTA, fused adjoint x pass (6 fields)
 
   static void fill(PassParams& p, smo_kdyn* h, int nf) {
     memset(&p, 0, sizeof p);

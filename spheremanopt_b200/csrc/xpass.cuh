@@ -18,6 +18,10 @@
 #pragma once
 #include "fft_core.cuh"
 
+#ifndef SMO_X_MB
+#define SMO_X_MB 2      // resident CTAs per SM the register allocation of the x passes is bounded for
+#endif
+
 namespace smo {
 
 struct XParams {
@@ -42,7 +46,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XPass {
   static constexpr int R1 = F::R1, R2 = F::R2, M = F::M, RT = F::RT;
   static constexpr int THREADS = NJ * RT;
   static constexpr int NPHASES = (MODE == X_C2R) ? 2 : 8;
-  static constexpr int MIN_BLOCKS = 1;
+  static constexpr int MIN_BLOCKS = SMO_X_MB;
   static constexpr int XLEN = (F::XP > FS::XP) ? ((F::XP > M) ? F::XP : M) : ((FS::XP > M) ? FS::XP : M);
   static constexpr size_t SMEM = (size_t)NJ * XLEN * sizeof(cplx);
   static_assert(T_ % 2 == 0, "columns are processed in pairs");

@@ -95,6 +95,8 @@ def _as_dev(domain, x):
     """-> (float64 CUDA tensor, was_devvec)"""
     if isinstance(x, DevVec):
         return x.t, True
+    if isinstance(x, torch.Tensor):
+        return x, True
     t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
     return t.to(domain.device, non_blocking=True), False
 

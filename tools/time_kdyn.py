@@ -7,10 +7,14 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from spheremanopt_b200 import _cabi, kdyn
+from spheremanopt_b200 import _cabi
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 nit = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+if len(sys.argv) > 3:
+    _cabi.LIB_PATH = sys.argv[3]   # a tuning variant built by tools/variants.py
+    print("library:", sys.argv[3])
+from spheremanopt_b200 import kdyn
 dom = kdyn.Domain(N)
 lib = dom.lib
 M = dom.M
