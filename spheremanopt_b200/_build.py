@@ -32,7 +32,7 @@ def _stale():
 
 def nvcc_command(out=OUT, extra=()):
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-DSMO_WITH_NCCL", "-o", out]
+           "-Xcompiler", "-fPIC", "-shared", "-Xlinker", "-Bsymbolic", "-DSMO_WITH_NCCL", "-o", out]
     cmd += list(extra)
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-ldl"]   # NCCL is dlopen'ed at run time (shares the host program's libnccl.so.2)

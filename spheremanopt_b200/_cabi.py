@@ -87,7 +87,7 @@ def load():
                 "spheremanopt_b200: CUDA library %s is missing - build it with "
                 "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
                 "There is no CPU fallback." % LIB_PATH)
-        _lib = bind(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
+        _lib = bind(C.CDLL(LIB_PATH))
     return _lib
 
 

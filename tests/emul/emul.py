@@ -34,7 +34,7 @@ def lib():
     if _lib is None:
         if _stale():
             os.makedirs(os.path.dirname(_OUT), exist_ok=True)
-            cmd = ["g++", "-O2", "-std=c++17", "-x", "c++", "-DSMO_EMUL", "-fPIC", "-shared", "-o", _OUT,
+            cmd = ["g++", "-O2", "-std=c++17", "-x", "c++", "-DSMO_EMUL", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-o", _OUT,
                    os.path.join(_CSRC, "smo_api.cu")]
             subprocess.run(cmd, check=True)
         _lib = _cabi.bind(C.CDLL(_OUT))

@@ -1,0 +1,109 @@
+"""CPU check of the kernels' index logic: the SAME phase bodies that nvcc compiles for sm_100a are compiled by g++
+(-DSMO_EMUL) and run thread-by-thread on the host, then compared with the oracle.  The emulation library is test
+infrastructure (tests/emul) and is never loaded by the product package."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import kdyn as okd
+from oracle import sh23 as osh
+from oracle import sphere as osp
+from tests.common import kdyn_field, relerr, sh23_input
+from tests.emul import emul
+
+TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def L():
+    return emul.lib()
+
+
+@pytest.mark.parametrize("Npts", [64, 128, 256])
+def test_sh23_emulated(L, Npts):
+    od = osh.domain_sh23(Npts)
+    batch, dt, nit = 6, 0.1, 12        # 6 instances: 4 per CTA -> one full and one ragged CTA
+    X = np.stack([sh23_input(od, seed=b, amp=0.04 + 0.003 * b) for b in range(batch)])
+    h = C.c_void_p()
+    emul.check(L.smo_sh23_create(C.byref(h), Npts, od.L, -0.3))
+    snaps = np.zeros((batch, nit + 1, od.Nh), dtype=complex)
+    J = np.zeros(batch); G = np.zeros((batch, od.M)); Gc = np.zeros((batch, od.M))
+    emul.check(L.smo_sh23_forward(h, emul.ptr(X), batch, dt, nit, emul.ptr(snaps), emul.ptr(J), None))
+    emul.check(L.smo_sh23_adjoint(h, batch, dt, nit, emul.ptr(snaps), emul.ptr(G), 0, None))
+    emul.check(L.smo_sh23_adjoint(h, batch, dt, nit, emul.ptr(snaps), emul.ptr(Gc), 1, None))
+    P = np.zeros((batch, od.M))
+    emul.check(L.smo_sh23_prep(h, emul.ptr(X), batch, 0.01, 5, emul.ptr(P), None))
+    for b in range(batch):
+        D = osh.GEN_BUFFER(od, nit)
+        fo = osh.FWD_Solve_IVP_Lin([X[b]], od, dt, nit, nit, D)
+        assert abs(-J[b] - fo) <= TOL * abs(fo)
+        assert relerr(snaps[b].T, D['A_fwd']) <= TOL
+        assert relerr(G[b], osh.ADJ_Solve_IVP_Lin([X[b]], od, dt, nit, nit, D)[0]) <= TOL
+        assert relerr(Gc[b], osh.ADJ_Solve_IVP_Lin([X[b]], od, dt, nit, nit, D, None, "Continuous")[0]) <= TOL
+        assert relerr(P[b], osh.FWD_Solve_IVP_PREP(X[b], od, 0.01, 5)) <= TOL
+    L.smo_sh23_destroy(h)
+
+
+@pytest.mark.parametrize("Npts,nit", [(16, 4), (24, 3), (32, 2)])
+def test_kdyn_emulated(L, Npts, nit):
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    if Npts == 16:   # adversarial input: not band limited, not solenoidal, non-zero mean
+        r = np.random.RandomState(3)
+        B0, U = r.standard_normal(B0.size), r.standard_normal(U.size)
+    h = C.c_void_p()
+    emul.check(L.smo_kdyn_create(C.byref(h), Npts, od.L, 0, 1, None))
+    csz, gsz = L.smo_kdyn_coef_elems(h), L.smo_kdyn_grid_elems(h)
+    assert gsz == od.M ** 3
+    coef = np.zeros((3, csz), dtype=complex)
+    emul.check(L.smo_kdyn_to_coef(h, emul.ptr(B0), emul.ptr(coef), None))
+    cc = coef.reshape(3, od.Nh, od.Nc, od.Nc + 1)[..., :od.Nc]
+    want = np.stack([od.to_coef_3d(x) for x in okd.Vec_to_Field(od, B0)])
+    assert relerr(cc, want) <= TOL
+    snaps = np.zeros(L.smo_kdyn_snapshot_bytes(h, nit) // 16, dtype=complex)
+    J = C.c_double()
+    Rm, dt = 2.0, 1e-3
+    emul.check(L.smo_kdyn_forward(h, emul.ptr(B0), emul.ptr(U), Rm, dt, nit, emul.ptr(snaps), C.byref(J), 0, None))
+    gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
+    emul.check(L.smo_kdyn_adjoint(h, Rm, dt, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), 0, None))
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    assert abs(-J.value - fo) <= TOL * abs(fo)
+    s = snaps.reshape(nit + 1, 3, od.Nh, od.Nc, od.Nc + 1)[..., :od.Nc]
+    assert relerr(np.transpose(s[:, 0], (1, 2, 3, 0)), D['A_fwd']) <= TOL
+    assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    if Npts == 24:
+        gBc, gUc = np.zeros(3 * gsz), np.zeros(3 * gsz)
+        emul.check(L.smo_kdyn_adjoint(h, Rm, dt, nit, emul.ptr(snaps), emul.ptr(gBc), emul.ptr(gUc), 1, None))
+        goc = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D, "Final", "Continuous")
+        assert relerr(gBc, goc[0]) <= TOL and relerr(gUc, goc[1]) <= TOL
+        out = np.zeros(3 * gsz)
+        emul.check(L.smo_kdyn_prep(h, emul.ptr(B0), emul.ptr(U), Rm, dt, 2, emul.ptr(out), None))
+        Bc = okd.FWD_Solve_IVP_Prep(B0, U, od, Rm, dt, 2)
+        assert relerr(out, okd.Field_to_Vec(od, *[od.to_grid_3d(c) for c in Bc])) <= TOL
+    L.smo_kdyn_destroy(h)
+
+
+def test_vector_kernels_emulated(L):
+    od = okd.domain_kdyn(16)
+    n = 3 * od.M ** 3
+    r = np.random.RandomState(0)
+    x, d = r.standard_normal(n), r.standard_normal(n)
+    work = np.zeros(L.smo_vec_work_bytes(n) // 8 + 1)
+    scale = 1.0 / od.M ** 3
+    out = C.c_double()
+    emul.check(L.smo_vec_dot(emul.ptr(x), emul.ptr(d), n, scale, C.byref(out), emul.ptr(work), None))
+    assert abs(out.value - okd.Inner_Prod_3(x, d, od)) <= 1e-13 * okd.Inner_Prod_3(x, x, od)
+    y = np.zeros(n)
+    emul.check(L.smo_vec_axpby(0.3, emul.ptr(x), -2.0, emul.ptr(d), emul.ptr(y), n, None))
+    assert relerr(y, 0.3 * x - 2.0 * d) <= 1e-15
+    emul.check(L.smo_vec_project(emul.ptr(x), emul.ptr(d), emul.ptr(y), n, emul.ptr(work), None))
+    assert relerr(y, osp.tangent_vector(x, d, okd.Inner_Prod_3, (od,))) <= 1e-13
+    emul.check(L.smo_vec_retract(emul.ptr(x), 0.7, emul.ptr(d), 2.5, scale, emul.ptr(y), n, emul.ptr(work), None))
+    assert relerr(y, osp.Update_vector(x, 0.7, d, 2.5, okd.Inner_Prod_3, (od,))) <= 1e-13
+    # ragged length (not a multiple of the chunk) and tiny vectors
+    for m in (1, 511, 8193):
+        emul.check(L.smo_vec_dot(emul.ptr(x), emul.ptr(d), m, 1.0, C.byref(out), emul.ptr(work), None))
+        assert abs(out.value - float(np.dot(x[:m], d[:m]))) <= 1e-12 * m
