@@ -771,9 +771,8 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   if (Nh % nranks || M % nranks) return fail(SMO_E_ARG, "nranks=%d must divide Npts/2=%d and 3*Npts/2=%d", nranks, Nh, M);
   if (nranks > 1 && !comm) return fail(SMO_E_ARG, "smo_kdyn_create: nranks > 1 needs a communicator");
   const int nz = M / nranks;
-  if (nz % 8) {
-    if (nranks > 1) return fail(SMO_E_ARG, "local z extent %d must be a multiple of 8", nz);
-  }
+  if (((long long)M * nz) % SMO_TX || ((long long)M * nz) % SMO_TXA)
+    return fail(SMO_E_ARG, "local grid columns M*nz = %lld must be a multiple of the x-pass tile (%d)", (long long)M * nz, SMO_TX);
   smo_kdyn* h = new smo_kdyn();
   h->N = Npts; h->M = M; h->Nh = Nh; h->kmax = (Npts - 1) / 2; h->Nc = 2 * h->kmax + 1; h->Pc = h->Nc + 1;
   h->L = L; h->kfac = 2.0 * 3.14159265358979323846 / L;
