@@ -5,11 +5,16 @@
 // access and solver.step (FWD_Solve_KDyn.py:635-641, 955-961): FFTW c2c along the axis plus the pad/truncate
 // copy between scales=1 and scales=3/2 ([D2-2], [D2-3] of SURVEY.md section 8(c)).
 //
-// A CTA handles a tile of T lines; each line is transformed by RT = max(R1,R2) threads in two register
-// stages with one shared-memory exchange (fft_core.cuh).  Global loads/stores go straight from/to registers:
-//   TFAST = true  : adjacent lines are adjacent in memory (strided axis); lanes run over the T lines so each
-//                   warp access covers T*16 B contiguous per FFT row.
-//   TFAST = false : the FFT axis itself is contiguous; lanes run over the stage threads of one line.
+// Structure (software-pipelined, HBM-bound):
+//   * a CTA owns tiles of T lines (persistent loop over tiles); the input tile of tile i+1 is streamed into
+//     shared memory with 16-byte asynchronous copies (cp.async / LDGSTS) while tile i is being transformed;
+//   * each line is transformed by RT = max(R1,R2) threads in two register stages (generated radix-R codelets)
+//     with one shared-memory exchange that re-uses the (already consumed) input buffer; twiddles come from a
+//     shared-memory table laid out so that every access is a compile-time offset from a per-thread base;
+//   * results go straight from registers to HBM; all per-element index arithmetic (padding map, truncation map,
+//     multi-rank segment map) is precomputed once per CTA, so the steady state has no integer divisions.
+//   TFAST = true  : adjacent lines are adjacent in memory (the y pass: FFT axis strided, lines along z);
+//   TFAST = false : the FFT axis itself is contiguous (the z pass).
 // Zero input rows (padding) are never loaded and dropped output rows (truncation) never stored, so HBM traffic
 // is the pruned C / P1 / P2 figure of SURVEY.md section 8(d).
 #pragma once
@@ -27,12 +32,12 @@ struct PassParams {
   cplx* out[MAXF];
   int nwork, nsteps;        // nwork = nfields * nA * tilesB, nsteps = 1
   int nfields, nA, nB, tilesB;
+  int b0;                   // first line index along B handled by this launch (chunked launches), lines b0 .. b0+nB-1
   long long in_sA, in_sB, out_sA, out_sB;   // line (a,b) base offsets, in complex elements
-  // full-length side (M entries):    off(n) = (n / split) * blk + (n % split) * sN
-  // compact side (2*kmax+1 entries): off(c) = c * sN
-  long long in_sN, out_sN, in_blk, out_blk;
-  int in_split, out_split;
-  int pad;                  // 1: input compact, output full (inverse direction); 0: input full, output compact
+  long long in_sN, out_sN;  // element stride along the FFT axis (1 when the axis is contiguous)
+  // full-length side of the z pass in the multi-rank P1 layout: off(n) = (n / seglen) * blk + (n % seglen)
+  int seglen;               // 0: no segmentation
+  long long blk;
   int kmax;
   double scale;             // applied to outputs
   const cplx* tw;           // exp(-2 pi i m / M), m < M
@@ -40,80 +45,158 @@ struct PassParams {
 
 template <class F, int DIR, bool TFAST, int T_> struct FftPass {
   typedef PassParams Params;
-  static constexpr int T = T_;
+  static constexpr bool V2 = true;
+  static constexpr bool PAD = DIR > 0;   // inverse direction: compact input, full-length output
+  static constexpr int T = T_, M = F::M, R1 = F::R1, R2 = F::R2, RT = F::RT;
+  static constexpr int KMAX = M / 3 - 1, NC = 2 * KMAX + 1;      // dealias 3/2: Npts = 2M/3, kmax = Npts/2 - 1
   static constexpr int THREADS = T_ * F::RT;
-  static constexpr int NPHASES = 2;
+  static constexpr int NPHASES = 4;
   static constexpr int MIN_BLOCKS = SMO_PASS_MB;
-  static constexpr size_t SMEM = (size_t)T_ * F::XP * sizeof(cplx);
+  // input tile: y pass [rows][T]; z pass [T][LENP]
+  static constexpr int NIN = PAD ? NC : M;
+  static constexpr int LENP = PAD ? NC + 1 : M;
+  static constexpr int IN_ELEMS = TFAST ? NIN * T_ : T_ * LENP;
+  static constexpr int X_ELEMS = T_ * F::XP;
+  static constexpr int BUF = (IN_ELEMS > X_ELEMS) ? IN_ELEMS : X_ELEMS;
+  static constexpr size_t SMEM = (size_t)(2 * BUF + M) * sizeof(cplx) + (size_t)M * sizeof(int);
   struct State {
     double re[F::RT], im[F::RT];
+    int ooff[F::R2];   // output offset of the k2-th result of this thread (complex elements), -1 = dropped
+    int it;            // tiles done by this CTA (buffer parity)
   };
 
-  SMO_HD static void decode(const Params& p, int work, int tid, int& f, int& a, int& b, int& t, int& jj) {
+  SMO_HD static cplx* buf(unsigned char* smem, int which) { return reinterpret_cast<cplx*>(smem) + (size_t)which * BUF; }
+  SMO_HD static cplx* twid(unsigned char* smem) { return reinterpret_cast<cplx*>(smem) + 2 * (size_t)BUF; }
+  SMO_HD static int* segtab(unsigned char* smem) { return reinterpret_cast<int*>(twid(smem) + M); }
+
+  SMO_HD static void split_tid(int tid, int& t, int& jj) {
+    if (TFAST) { t = tid % T; jj = tid / T; } else { jj = tid % RT; t = tid / RT; }
+  }
+  SMO_HD static void decode(const Params& p, int work, int& f, int& a, int& bt) {
     const int per_field = p.nA * p.tilesB;
     f = work / per_field;
     const int r = work - f * per_field;
     a = r / p.tilesB;
-    const int bt = r - a * p.tilesB;
-    if (TFAST) { t = tid % T; jj = tid / T; } else { jj = tid % F::RT; t = tid / F::RT; }
-    b = bt * T + t;
+    bt = r - a * p.tilesB;
   }
   SMO_HD static int xidx(int t, int e) { return TFAST ? e * T + t : t * F::XP + e; }
+  // offset of full-length index n on a (possibly segmented) side
+  SMO_HD static long long full_off(const Params& p, int n, long long sN) {
+    if (!TFAST && p.seglen > 0) return (long long)(n / p.seglen) * p.blk + (long long)(n % p.seglen);
+    return (long long)n * sN;
+  }
+
+  // stream the input tile of `work` into buffer `which` (asynchronous)
+  SMO_HD static void load_tile(const Params& p, int work, int which, const Ctx& c) {
+    int f, a, bt, t, jj;
+    decode(p, work, f, a, bt);
+    split_tid(c.tid, t, jj);
+    cplx* B = buf(c.smem, which);
+    const int b = bt * T + t;   // line within this launch
+    if (b < p.nB) {
+      const cplx* src = p.in[f] + (long long)a * p.in_sA + (long long)(p.b0 + b) * p.in_sB;
+      if (TFAST) {
+        // rows of T adjacent lines: lane t walks along z (16 B each, T*16 B contiguous per row)
+        for (int row = jj; row < NIN; row += RT) cp_async16(&B[row * T + t], src + (long long)row * p.in_sN);
+      } else if (PAD || p.seglen <= 0) {
+        for (int e = jj; e < LENP; e += RT) cp_async16(&B[t * LENP + e], src + e);
+      } else {
+        const int* so = segtab(c.smem);
+        for (int e = jj; e < LENP; e += RT) cp_async16(&B[t * LENP + e], src + so[e]);
+      }
+    }
+  }
+
+  SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
+    int t, jj;
+    split_tid(c.tid, t, jj);
+    cplx* W = twid(c.smem);
+    // twiddle table [k1][j]: w_M^(j*k1); a stage-1 thread reads W[k1*R2 + j] (compile-time offsets from W + j)
+    for (int m = c.tid; m < M; m += THREADS) W[m] = ldg_c(p.tw + ((m % R2) * (m / R2)) % M);
+    if (!TFAST) {
+      int* so = segtab(c.smem);
+      for (int m = c.tid; m < M; m += THREADS) so[m] = (int)full_off(p, m, 1);
+    }
+    // per-thread output map of stage 2 (thread k1 = jj holds X[k1 + R1*k2])
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) {
+      const int k = jj + R1 * k2;
+      int off = -1;
+      if (jj < R1) {
+        if (PAD) off = (int)full_off(p, k, p.out_sN);
+        else { const int cidx = compact_index(k, M, KMAX); if (cidx >= 0) off = (int)((long long)cidx * p.out_sN); }
+      }
+      st.ooff[k2] = off;
+    }
+    st.it = 0;
+  }
 
   template <int PH>
-  SMO_HD static void phase(const Params& p, int work, int /*step*/, int tid, unsigned char* smem, State& st) {
-    cplx* X = reinterpret_cast<cplx*>(smem);
-    int f, a, b, t, jj;
-    decode(p, work, tid, f, a, b, t, jj);
-    const bool live = b < p.nB;
-    constexpr int M = F::M;
+  SMO_HD static void phase2(const Params& p, int work, int /*step*/, const Ctx& c, State& st) {
+    int t, jj;
+    split_tid(c.tid, t, jj);
+    const int cur = st.it & 1;
+    cplx* B = buf(c.smem, cur);
     if (PH == 0) {
-      if (jj < F::R2) {
+      // (first tile of this CTA: start its own stream;) prefetch the next tile of this CTA into the other buffer,
+      // then wait for the current one
+      if (st.it == 0) { load_tile(p, work, cur, c); cp_async_commit(); }
+      if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, cur ^ 1, c);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else if (PH == 1) {
+      if (jj < R2) {
         const int j = jj;
-        const cplx* src = p.in[f] + (long long)a * p.in_sA + (long long)b * p.in_sB;
 #pragma unroll
-        for (int i = 0; i < F::R1; ++i) {
-          const int n = j + F::R2 * i;
-          double vr = 0.0, vi = 0.0;
-          if (live) {
-            if (p.pad) {
-              const int c = compact_index(n, M, p.kmax);
-              if (c >= 0) { const cplx v = src[(long long)c * p.in_sN]; vr = v.x; vi = v.y; }
-            } else {
-              const cplx v = src[(long long)(n / p.in_split) * p.in_blk + (long long)(n % p.in_split) * p.in_sN];
-              vr = v.x; vi = v.y;
-            }
+        for (int i = 0; i < R1; ++i) {
+          const int n = j + R2 * i;
+          int row = n;
+          bool nz = true;
+          if (PAD) {
+            if (n > KMAX) { row = n - (M - NC); nz = (n >= M - KMAX); }
           }
-          st.re[i] = vr; st.im[i] = vi;
+          cplx v = make_double2(0.0, 0.0);
+          if (nz) v = TFAST ? B[row * T + t] : B[t * LENP + row];
+          st.re[i] = v.x; st.im[i] = v.y;
         }
-        stage1<F, DIR>(st.re, st.im, j, p.tw);
+        const cplx* W = twid(c.smem) + j;
+        RegFFT<R1, DIR>::run(as_arr<R1>(st.re), as_arr<R1>(st.im));
 #pragma unroll
-        for (int k1 = 0; k1 < F::R1; ++k1) X[xidx(t, j * F::SK + k1)] = make_double2(st.re[k1], st.im[k1]);
+        for (int k1 = 1; k1 < R1; ++k1) {
+          const cplx w = W[k1 * R2];
+          const double cc = w.x, ss = (DIR > 0) ? -w.y : w.y;
+          const double a = st.re[k1], b = st.im[k1];
+          st.re[k1] = a * cc - b * ss;
+          st.im[k1] = a * ss + b * cc;
+        }
+      }
+    } else if (PH == 2) {
+      if (jj < R2) {
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) B[xidx(t, jj * F::SK + k1)] = make_double2(st.re[k1], st.im[k1]);
       }
     } else {
-      if (jj < F::R1) {
+      if (jj < R1) {
         const int k1 = jj;
 #pragma unroll
-        for (int j = 0; j < F::R2; ++j) {
-          const cplx v = X[xidx(t, j * F::SK + k1)];
+        for (int j = 0; j < R2; ++j) {
+          const cplx v = B[xidx(t, j * F::SK + k1)];
           st.re[j] = v.x; st.im[j] = v.y;
         }
         stage2<F, DIR>(st.re, st.im);
-        if (live) {
-          cplx* dst = p.out[f] + (long long)a * p.out_sA + (long long)b * p.out_sB;
+        int f, a, bt;
+        decode(p, work, f, a, bt);
+        const int b = bt * T + t;
+        if (b < p.nB) {
+          cplx* dst = p.out[f] + (long long)a * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
 #pragma unroll
-          for (int k2 = 0; k2 < F::R2; ++k2) {
-            const int k = k1 + F::R1 * k2;
-            const cplx v = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
-            if (p.pad) {
-              dst[(long long)(k / p.out_split) * p.out_blk + (long long)(k % p.out_split) * p.out_sN] = v;
-            } else {
-              const int c = compact_index(k, M, p.kmax);
-              if (c >= 0) dst[(long long)c * p.out_sN] = v;
-            }
+          for (int k2 = 0; k2 < R2; ++k2) {
+            const int off = st.ooff[k2];
+            if (PAD || off >= 0) dst[off] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
           }
         }
       }
+      st.it++;
     }
   }
 };

@@ -528,15 +528,16 @@ template <int M> struct KdOps {
   static void fill(PassParams& p, smo_kdyn* h, int nf) {
     memset(&p, 0, sizeof p);
     p.nfields = nf; p.nsteps = 1; p.kmax = h->kmax; p.tw = h->tw; p.scale = 1.0;
-    p.in_split = p.out_split = M; p.in_blk = p.out_blk = 0;
+    p.in_sN = p.out_sN = 1; p.seglen = 0; p.blk = 0; p.b0 = 0;
   }
   // coefficient [nkx][Nc][Pc] -> p1 [s][nkx][Nc][nz]   (zero-pad + inverse FFT along z)
   static int inv_z(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
     PassParams p; fill(p, h, nf);
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
-    p.pad = 1; p.nA = 1; p.nB = h->nkx * h->Nc; p.tilesB = (p.nB + TZ - 1) / TZ;
-    p.in_sA = 0; p.in_sB = h->Pc; p.in_sN = 1;
-    p.out_sA = 0; p.out_sB = h->nz; p.out_sN = 1; p.out_split = h->nz; p.out_blk = (long long)h->nkx * h->Nc * h->nz;
+    p.nA = 1; p.nB = h->nkx * h->Nc; p.tilesB = (p.nB + TZ - 1) / TZ;
+    p.in_sA = 0; p.in_sB = h->Pc;
+    p.out_sA = 0; p.out_sB = h->nz;
+    if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Z, st);
     int rc = launch<FftPass<F, +1, false, TZ>>(p, st);
@@ -547,9 +548,10 @@ template <int M> struct KdOps {
   static int fwd_z(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
     PassParams p; fill(p, h, nf);
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
-    p.pad = 0; p.nA = 1; p.nB = h->nkx * h->Nc; p.tilesB = (p.nB + TZ - 1) / TZ;
-    p.in_sA = 0; p.in_sB = h->nz; p.in_sN = 1; p.in_split = h->nz; p.in_blk = (long long)h->nkx * h->Nc * h->nz;
-    p.out_sA = 0; p.out_sB = h->Pc; p.out_sN = 1;
+    p.nA = 1; p.nB = h->nkx * h->Nc; p.tilesB = (p.nB + TZ - 1) / TZ;
+    p.in_sA = 0; p.in_sB = h->nz;
+    if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
+    p.out_sA = 0; p.out_sB = h->Pc;
     p.scale = 1.0 / M;
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Z, st);
@@ -557,11 +559,11 @@ template <int M> struct KdOps {
     prof_end(h, PK_Z, st);
     return rc;
   }
-  // p1t [Nh][Nc][nz] -> p2 [Nh][M][nz]   (zero-pad + inverse FFT along y)
-  static int inv_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
+  // p1t [Nh][Nc][nz] -> p2 [Nh][M][nz]   (zero-pad + inverse FFT along y) for the z range [z0, z0+nzc)
+  static int inv_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1) {
     PassParams p; fill(p, h, nf);
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
-    p.pad = 1; p.nA = h->Nh; p.nB = h->nz; p.tilesB = (p.nB + TY - 1) / TY;
+    p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
     p.in_sA = (long long)h->Nc * h->nz; p.in_sB = 1; p.in_sN = h->nz;
     p.out_sA = (long long)M * h->nz; p.out_sB = 1; p.out_sN = h->nz;
     p.nwork = nf * p.nA * p.tilesB;
@@ -570,10 +572,10 @@ template <int M> struct KdOps {
     prof_end(h, PK_Y, st);
     return rc;
   }
-  static int fwd_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
+  static int fwd_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1) {
     PassParams p; fill(p, h, nf);
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
-    p.pad = 0; p.nA = h->Nh; p.nB = h->nz; p.tilesB = (p.nB + TY - 1) / TY;
+    p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
     p.in_sA = (long long)M * h->nz; p.in_sB = 1; p.in_sN = h->nz;
     p.out_sA = (long long)h->Nc * h->nz; p.out_sB = 1; p.out_sN = h->nz;
     p.scale = 1.0 / M;

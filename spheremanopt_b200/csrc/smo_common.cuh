@@ -49,6 +49,33 @@ SMO_HD cplx ldg_c(const cplx* p) {
 #endif
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2-only caching): the producer side of the software pipelines.
+// Host emulation: an immediate copy.
+SMO_HD void cp_async16(void* sdst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+#else
+  memcpy(sdst, gsrc, 16);
+#endif
+}
+SMO_HD void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N> SMO_HD void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// what a CTA knows about itself (kernels with K::V2 == true get this instead of a bare tid / smem pair)
+struct Ctx {
+  int cta, ncta, tid;
+  unsigned char* smem;
+};
+
 SMO_HD int imax(int a, int b) { return a > b ? a : b; }
 SMO_HD int imin(int a, int b) { return a < b ? a : b; }
 
@@ -60,12 +87,21 @@ SMO_HD int imin(int a, int b) { return a < b ? a : b; }
 //   static constexpr int THREADS, NPHASES, MIN_BLOCKS;
 //   template <int PH> SMO_HD static void phase(const Params&, int work, int step, int tid, unsigned char* smem, State&);
 // For every work item the runner executes  for step in [0,nsteps): phase<0>, sync, phase<1>, sync, ...
+// kernels that define `static constexpr bool V2 = true` use the Ctx interface (init + phase2)
+template <class K, class = void> struct is_v2 { static constexpr bool value = false; };
+template <class K> struct is_v2<K, decltype((void)K::V2)> { static constexpr bool value = K::V2; };
+
 #if !defined(SMO_EMUL)
 template <class K, int PH, bool END> struct PhaseStep;
 template <class K, int PH> struct PhaseStep<K, PH, false> {
   static __device__ __forceinline__ void run(const typename K::Params& p, int work, int step, int tid,
                                              unsigned char* smem, typename K::State& st) {
-    K::template phase<PH>(p, work, step, tid, smem, st);
+    if constexpr (is_v2<K>::value) {
+      Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = tid; c.smem = smem;
+      K::template phase2<PH>(p, work, step, c, st);
+    } else {
+      K::template phase<PH>(p, work, step, tid, smem, st);
+    }
     __syncthreads();
     PhaseStep<K, PH + 1, (PH + 1 >= K::NPHASES)>::run(p, work, step, tid, smem, st);
   }
@@ -80,17 +116,30 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const typename K::Params p) {
   extern __shared__ __align__(16) unsigned char smo_smem[];
   typename K::State st;
+  if constexpr (is_v2<K>::value) {
+    Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
+    K::init(p, c, st);
+    __syncthreads();
+  }
   for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
     for (int step = 0; step < p.nsteps; ++step)
       PhaseStep<K, 0, false>::run(p, work, step, (int)threadIdx.x, smo_smem, st);
   }
 }
 #else
+static thread_local int g_emul_cta = 0, g_emul_ncta = 1;
 template <class K, int PH, bool END> struct EmulStep;
 template <class K, int PH> struct EmulStep<K, PH, false> {
   static void run(const typename K::Params& p, int work, int step, unsigned char* smem,
                   std::vector<typename K::State>& st) {
-    for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<PH>(p, work, step, tid, smem, st[tid]);
+    for (int tid = 0; tid < K::THREADS; ++tid) {
+      if constexpr (is_v2<K>::value) {
+        Ctx c; c.cta = g_emul_cta; c.ncta = g_emul_ncta; c.tid = tid; c.smem = smem;
+        K::template phase2<PH>(p, work, step, c, st[tid]);
+      } else {
+        K::template phase<PH>(p, work, step, tid, smem, st[tid]);
+      }
+    }
     EmulStep<K, PH + 1, (PH + 1 >= K::NPHASES)>::run(p, work, step, smem, st);
   }
 };
@@ -103,9 +152,17 @@ template <class K> void emul_kernel(int grid, size_t smem_bytes, const typename 
   unsigned char* sm = smem.data();
   sm += (16 - ((uintptr_t)sm & 15)) & 15;
   std::vector<typename K::State> st(K::THREADS);
-  for (int cta = 0; cta < grid; ++cta)
+  for (int cta = 0; cta < grid; ++cta) {
+    g_emul_cta = cta; g_emul_ncta = grid;
+    if constexpr (is_v2<K>::value) {
+      for (int tid = 0; tid < K::THREADS; ++tid) {
+        Ctx c; c.cta = cta; c.ncta = grid; c.tid = tid; c.smem = sm;
+        K::init(p, c, st[tid]);
+      }
+    }
     for (int work = cta; work < p.nwork; work += grid)
       for (int step = 0; step < p.nsteps; ++step) EmulStep<K, 0, false>::run(p, work, step, sm, st);
+  }
 }
 #endif
 
