@@ -106,10 +106,13 @@ int smo_kdyn_prep_host(smo_kdyn_t* h, const double* B0_host, const double* U_hos
 /* transform helpers (tests, initial conditions): grid [3][grid_elems] <-> coefficients [3][coef_elems] */
 int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid_dev, void* coef_dev, void* stream);
 int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef_dev, double* grid_dev, void* stream);
-/* per-kernel timing of the time loops: which = 0 off, 1..5 = z-pass, y-pass, fused x-pass, epilogue, all-to-all.
+/* per-kernel timing of the time loops: which = 0 off, 1..6 = z-pass, y-pass, fused forward x-pass, epilogue, all-to-all, fused adjoint x-pass.
  * smo_kdyn_profile_read returns the accumulated CUDA-event time (ms) and launch count since the last set. */
 int smo_kdyn_profile_set(smo_kdyn_t* h, int which);
 int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long* launches);
+/* tuning: number of z chunks of the y-pass -> fused x-pass -> y-pass sequence of a forward / adjoint step (keeps the
+ * y-padded arrays L2 resident); -1 = choose from the problem size (default), 1 = off */
+int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);
 

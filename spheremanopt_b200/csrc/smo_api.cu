@@ -424,6 +424,7 @@ struct smo_kdyn {
   cplx* cw[MAXF];    // coefficient work
   cplx* G[3]; cplx* NU[3]; cplx* W[3];
   double* Ug[3];     // projected velocity on the grid [M][M][nz]
+  double* Ut;        // the same, tile-major [M*nz/4][3][M][4] (read by the fused x passes)
   double* gwork;     // 3*gsize doubles
   double* vwork;     // reduction workspace
   bool have_U;
@@ -437,9 +438,10 @@ struct smo_kdyn {
   size_t ev_used;
 #endif
   int use_graph;
+  int chunks_fwd, chunks_adj;   // z-chunked y/x/y sequence (L2-resident P2 arrays); <= 1: whole slab at once
 };
 
-enum { PK_Z = 1, PK_Y = 2, PK_X = 3, PK_EPI = 4, PK_A2A = 5 };
+enum { PK_Z = 1, PK_Y = 2, PK_X = 3, PK_EPI = 4, PK_A2A = 5, PK_XA = 6 };
 
 #if !defined(SMO_EMUL)
 static void prof_begin(smo_kdyn* h, int kind, rt_stream st) {
@@ -600,22 +602,49 @@ template <int M> struct KdOps {
     for (int f = 0; f < 3; ++f) { p.gin[f] = in[f]; p.sout[f] = out[f]; }
     return launch<XPass<F, TX, X_R2C, 3, 3>>(p, st);
   }
-  static int x_fwd(smo_kdyn* h, cplx* const* io, rt_stream st) {
-    XParams p; xfill(p, h, TX);
-    for (int f = 0; f < 3; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; p.gin[f] = h->Ug[f]; }
+  // number of z chunks for the y -> x -> y sequence: the P2 arrays of one chunk (nf fields) should stay L2 resident
+  // (~126 MB L2: aim at <= 32 MB per chunk); every chunk must hold whole tiles and still fill the GPU
+  static int pick_chunks(smo_kdyn* h, int requested, int nf, int tile) {
+    int nch = requested;
+    if (nch < 0) {
+      const double bytes = (double)nf * h->p2size * sizeof(cplx);
+      nch = (int)(bytes / (32.0 * 1024 * 1024) + 0.999);
+    }
+    if (nch < 1) nch = 1;
+    while (nch > 1 && (h->nz % nch != 0 || (h->nz / nch) % tile != 0 || (h->nz / nch) % TY != 0)) --nch;
+    return nch;
+  }
+  static void xffill(XFParams& p, smo_kdyn* h, int T, int z0, int nzc) {
+    memset(&p, 0, sizeof p);
+    p.nsteps = 1; p.ncols = (long long)M * h->nz; p.Nh = h->Nh; p.tw = h->tw; p.scale = 1.0 / M; p.ut = h->Ut;
+    if (nzc < 0) {   // all columns: tiles of T consecutive (y,z) columns, may straddle rows
+      p.tiles_per_row = (int)(p.ncols / T); p.row_tiles = 0; p.tile0 = 0; p.nwork = p.tiles_per_row;
+    } else {         // z range [z0, z0+nzc) of every row (needs nz, z0, nzc multiples of T)
+      p.tiles_per_row = nzc / T; p.row_tiles = h->nz / T; p.tile0 = z0 / T; p.nwork = M * p.tiles_per_row;
+    }
+  }
+  static int x_fwd(smo_kdyn* h, cplx* const* io, rt_stream st, int z0 = 0, int nzc = -1) {
+    XFParams p; xffill(p, h, TX, z0, nzc);
+    for (int f = 0; f < 3; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
     prof_begin(h, PK_X, st);
-    int rc = launch<XPass<F, TX, X_FWD, 3, 3>>(p, st);
+    int rc = launch<XFused<F, TX, X_FWD, 3, 3>>(p, st);
     prof_end(h, PK_X, st);
     return rc;
   }
-  static int x_adj(smo_kdyn* h, cplx* const* io, rt_stream st) {
-    XParams p; xfill(p, h, TXA);
+  static int x_adj(smo_kdyn* h, cplx* const* io, rt_stream st, int z0 = 0, int nzc = -1) {
+    XFParams p; xffill(p, h, TXA, z0, nzc);
     for (int f = 0; f < 6; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
-    for (int f = 0; f < 3; ++f) p.gin[f] = h->Ug[f];
-    prof_begin(h, PK_X, st);
-    int rc = launch<XPass<F, TXA, X_ADJ, 6, 6>>(p, st);
-    prof_end(h, PK_X, st);
+    prof_begin(h, PK_XA, st);
+    int rc = launch<XFused<F, TXA, X_ADJ, 6, 6>>(p, st);
+    prof_end(h, PK_XA, st);
     return rc;
+  }
+  static int u_tile(smo_kdyn* h, rt_stream st) {
+    UTileParams p; memset(&p, 0, sizeof p);
+    for (int c = 0; c < 3; ++c) p.in[c] = h->Ug[c];
+    p.out = h->Ut; p.ncols = (long long)M * h->nz; p.M = M; p.nsteps = 1;
+    p.nwork = (int)(M * ((p.ncols + UTile::THREADS - 1) / UTile::THREADS));
+    return launch<UTile>(p, st);
   }
 
   // grid [3][gsize] -> coefficients [3][csize]
@@ -643,9 +672,14 @@ template <int M> struct KdOps {
   static int fwd_step(smo_kdyn* h, const cplx* const* Bn, cplx* const* Bnp1, double Rm, double dt, rt_stream st) {
     TRY(inv_z(h, Bn, h->p1, 3, st));
     TRY(a2a(h, h->p1, h->p1t, 3, st));
-    TRY(inv_y(h, h->p1t, h->p2, 3, st));
-    TRY(x_fwd(h, h->p2, st));
-    TRY(fwd_y(h, h->p2, h->p1t, 3, st));
+    const int nch = pick_chunks(h, h->chunks_fwd, 3, TX);
+    const int nzc = h->nz / nch;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int z0 = ch * nzc;
+      TRY(inv_y(h, h->p1t, h->p2, 3, st, z0, nch > 1 ? nzc : -1));
+      TRY(x_fwd(h, h->p2, st, z0, nch > 1 ? nzc : -1));
+      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, nch > 1 ? nzc : -1));
+    }
     TRY(a2a(h, h->p1t, h->p1, 3, st));
     TRY(fwd_z(h, h->p1, h->cw, 3, st));
     EpiParams e; efill(e, h, Rm, dt, 0);
@@ -660,9 +694,14 @@ template <int M> struct KdOps {
     const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], Bf[0], Bf[1], Bf[2]};
     TRY(inv_z(h, in6, h->p1, 6, st));
     TRY(a2a(h, h->p1, h->p1t, 6, st));
-    TRY(inv_y(h, h->p1t, h->p2, 6, st));
-    TRY(x_adj(h, h->p2, st));
-    TRY(fwd_y(h, h->p2, h->p1t, 6, st));
+    const int nch = pick_chunks(h, h->chunks_adj, 6, TXA > TY ? TXA : TY);
+    const int nzc = h->nz / nch;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int z0 = ch * nzc;
+      TRY(inv_y(h, h->p1t, h->p2, 6, st, z0, nch > 1 ? nzc : -1));
+      TRY(x_adj(h, h->p2, st, z0, nch > 1 ? nzc : -1));
+      TRY(fwd_y(h, h->p2, h->p1t, 6, st, z0, nch > 1 ? nzc : -1));
+    }
     TRY(a2a(h, h->p1t, h->p1, 6, st));
     TRY(fwd_z(h, h->p1, h->cw, 6, st));
     EpiParams e; efill(e, h, Rm, dt, flag);
@@ -701,6 +740,7 @@ template <int M> static int kd_set_U(smo_kdyn* h, const double* U, rt_stream st)
   double* g = h->gwork;
   TRY(KdOps<M>::to_grid(h, h->cw, g, st));
   for (int c = 0; c < 3; ++c) TRY(rt_d2d(h->Ug[c], g + (size_t)c * h->gsize, sizeof(double) * h->gsize, st));
+  TRY(KdOps<M>::u_tile(h, st));
   h->have_U = true;
   return 0;
 }
@@ -774,7 +814,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   if (nranks > 1 && !comm) return fail(SMO_E_ARG, "smo_kdyn_create: nranks > 1 needs a communicator");
   const int nz = M / nranks;
   if (((long long)M * nz) % SMO_TX || ((long long)M * nz) % SMO_TXA)
-    return fail(SMO_E_ARG, "local grid columns M*nz = %lld must be a multiple of the x-pass tile (%d)", (long long)M * nz, SMO_TX);
+    return fail(SMO_E_ARG, "local grid columns M*nz = %lld must be a multiple of the x-pass tiles (%d, %d)", (long long)M * nz, SMO_TX, SMO_TXA);
   smo_kdyn* h = new smo_kdyn();
   h->N = Npts; h->M = M; h->Nh = Nh; h->kmax = (Npts - 1) / 2; h->Nc = 2 * h->kmax + 1; h->Pc = h->Nc + 1;
   h->L = L; h->kfac = 2.0 * 3.14159265358979323846 / L;
@@ -786,10 +826,12 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->comm = comm;
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
+  h->chunks_fwd = h->chunks_adj = -1;   // -1: choose from the problem size
   h->hB = h->hU = h->hGB = h->hGU = nullptr; h->snaps = nullptr; h->cap_snap = 0;
   h->tw = nullptr; h->gwork = nullptr; h->vwork = nullptr;
   for (int f = 0; f < MAXF; ++f) h->p1[f] = h->p1t[f] = h->p2[f] = h->cw[f] = nullptr;
   for (int c = 0; c < 3; ++c) { h->G[c] = h->NU[c] = h->W[c] = nullptr; h->Ug[c] = nullptr; }
+  h->Ut = nullptr;
 #if !defined(SMO_EMUL)
   h->ev = new std::vector<cudaEvent_t>(); h->ev_used = 0;
 #endif
@@ -810,6 +852,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
     if (rc == 0) rc = rt_malloc((void**)&h->W[c], sizeof(cplx) * h->csize);
     if (rc == 0) rc = rt_malloc((void**)&h->Ug[c], sizeof(double) * h->gsize);
   }
+  if (rc == 0) rc = rt_malloc((void**)&h->Ut, sizeof(double) * 3 * h->gsize);
   if (rc == 0) rc = rt_malloc((void**)&h->gwork, sizeof(double) * 3 * h->gsize);
   if (rc == 0) rc = rt_malloc((void**)&h->vwork, smo_vec_work_bytes((long long)(3 * h->gsize)));
   if (rc) { smo_kdyn_destroy(h); return rc; }
@@ -824,7 +867,7 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
     rt_free(h->p1[f]); rt_free(h->p2[f]); rt_free(h->cw[f]);
   }
   for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); }
-  rt_free(h->gwork); rt_free(h->vwork);
+  rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut);
   rt_free(h->hB); rt_free(h->hU); rt_free(h->hGB); rt_free(h->hGU); rt_free(h->snaps);
 #if !defined(SMO_EMUL)
   if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
@@ -925,6 +968,11 @@ extern "C" int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long*
   if (!h) return fail(SMO_E_ARG, "smo_kdyn_profile_read: null handle");
   if (total_ms) *total_ms = h->prof_ms;
   if (launches) *launches = h->prof_n;
+  return 0;
+}
+extern "C" int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj) {
+  if (!h) return fail(SMO_E_ARG, "smo_kdyn_set_chunks: null handle");
+  h->chunks_fwd = chunks_fwd; h->chunks_adj = chunks_adj;
   return 0;
 }
 extern "C" int smo_kdyn_use_graph(smo_kdyn_t* h, int on) {

@@ -198,4 +198,272 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XPass {
   }
 };
 
+
+// ================================================================================================================
+// Fused x-pass of the time loops, software pipelined (X_FWD: U x B; X_ADJ: (curl G) x U and (curl G) x B_f).
+//
+// Same mathematics as XPass above, restructured for HBM throughput:
+//   * the spectral input tile (NFI fields x Nh rows x T columns) and the velocity tile (3 x M x T doubles) of the
+//     NEXT column tile are streamed into shared memory with cp.async while the current tile is transformed (the
+//     spectral buffer is free after the assembly phase, the velocity buffer after the product phase);
+//   * the velocity field is read from a tile-major copy Ut[ncols/4][3][M][4] written once per forward call, so a
+//     tile's velocity data is one contiguous 18 KB block per 4 columns (perfectly coalesced, no 32-byte rows);
+//   * column tiles can be restricted to a z range (chunked launches keep the P2 arrays L2-resident between the
+//     y pass that produces them, this kernel and the y pass that consumes its output).
+// Phases: 0 wait spectral tile | 1 assemble + inverse stage 1 | 2 prefetch next spectral tile, inverse stage 2 |
+//   3 grid values -> shared, wait velocity tile | 4 products + forward stage 1 | 5 prefetch next velocity tile,
+//   exchange | 6 forward stage 2 | 7 spectrum -> shared | 8 split, scale, truncate, store.
+// ================================================================================================================
+struct XFParams {
+  const cplx* sin[MAXF];     // spectral inputs  [Nh][ncols]
+  cplx* sout[MAXF];          // spectral outputs [Nh][ncols]
+  const double* ut;          // velocity, tile-major [ncols/4][3][M][4]
+  int nwork, nsteps;         // nwork = number of column tiles of this launch
+  long long ncols;
+  int Nh;
+  int tiles_per_row, row_tiles, tile0;   // column tile of work w: (w / tiles_per_row) * row_tiles + tile0 + w % tiles_per_row
+  double scale;
+  const cplx* tw;
+};
+
+template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
+  typedef XFParams Params;
+  typedef typename F::Swapped FS;
+  static constexpr bool V2 = true;
+  static constexpr int T = T_, HP = T_ / 2, TB = T_ / 4;
+  static constexpr int NJI = NFI * HP, NJO = NFO * HP, NJ = (NJI > NJO) ? NJI : NJO;
+  static constexpr int R1 = F::R1, R2 = F::R2, M = F::M, RT = F::RT;
+  static constexpr int NH = M / 3;                   // retained kx modes (dealias 3/2: Npts/2 = M/3)
+  static constexpr int THREADS = NJ * RT;
+  static constexpr int NPHASES = 9;
+  static constexpr int MIN_BLOCKS = SMO_X_MB;
+  static constexpr int XLEN = (F::XP > FS::XP) ? ((F::XP > M) ? F::XP : M) : ((FS::XP > M) ? FS::XP : M);
+  static constexpr int SP = T_ + 1;                  // pitch of a spectral row in shared memory (bank spread)
+  static constexpr int SIN_ELEMS = NFI * NH * SP;    // cplx
+  static constexpr int SU_DOUBLES = 3 * M * T_;
+  static constexpr int X_ELEMS = NJ * XLEN;
+  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + X_ELEMS + 2 * M) * sizeof(cplx) + (size_t)SU_DOUBLES * sizeof(double);
+  static_assert(T_ % 4 == 0, "column tiles are multiples of the 4-column velocity blocks");
+  static_assert(MODE == X_FWD || MODE == X_ADJ, "fused modes only");
+  struct State {
+    double re[RT], im[RT];
+    int it;
+  };
+
+  SMO_HD static cplx* sin_buf(unsigned char* s) { return reinterpret_cast<cplx*>(s); }
+  SMO_HD static cplx* x_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
+  SMO_HD static cplx* tw1(unsigned char* s) { return x_buf(s) + X_ELEMS; }        // inverse stage twiddles [k1][j]  (R1 x R2)
+  SMO_HD static cplx* tw2(unsigned char* s) { return tw1(s) + M; }               // forward (swapped) stage twiddles [k1][j]  (R2 x R1)
+  SMO_HD static double* su_buf(unsigned char* s) { return reinterpret_cast<double*>(tw2(s) + M); }
+
+  SMO_HD static void decode(int tid, int& f, int& pp, int& jj) {
+    pp = tid % HP;
+    jj = (tid / HP) % RT;
+    f = tid / (HP * RT);
+  }
+  SMO_HD static long long tile_of(const Params& p, int work) {
+    return (long long)(work / p.tiles_per_row) * p.row_tiles + p.tile0 + (work % p.tiles_per_row);
+  }
+  // asynchronous loads of the spectral tile / the velocity tile of `work`
+  SMO_HD static void load_sin(const Params& p, int work, const Ctx& c) {
+    cplx* S = sin_buf(c.smem);
+    const long long col0 = tile_of(p, work) * T;
+    // chunks: (f, row, tcol); lanes run over tcol fastest
+    for (int q = c.tid; q < NFI * NH * T; q += THREADS) {
+      const int tc = q % T, r = q / T;
+      const int row = r % NH, f = r / NH;
+      cp_async16(&S[(f * NH + row) * SP + tc], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+    }
+  }
+  SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
+    double* U = su_buf(c.smem);
+    const double* src = p.ut + tile_of(p, work) * TB * (3LL * M * 4);
+    for (int q = c.tid; q < SU_DOUBLES / 2; q += THREADS) cp_async16(&U[2 * q], src + 2 * q);
+  }
+  // velocity pair (columns 2pp, 2pp+1 of the tile) of component cidx at grid row n
+  SMO_HD static cplx su_pair(const double* U, int cidx, int n, int pp) {
+    const int blk = pp / 2, w = (pp % 2) * 2;
+    const double* q = U + ((blk * 3 + cidx) * M + n) * 4 + w;
+    return make_double2(q[0], q[1]);
+  }
+
+  SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
+    cplx* W1 = tw1(c.smem);
+    cplx* W2 = tw2(c.smem);
+    for (int m = c.tid; m < M; m += THREADS) {
+      W1[m] = ldg_c(p.tw + ((m % R2) * (m / R2)) % M);   // [k1 < R1][j < R2]
+      W2[m] = ldg_c(p.tw + ((m % R1) * (m / R1)) % M);   // [k1 < R2][j < R1]
+    }
+    st.it = 0;
+  }
+
+  // product needed by output field fo at grid row n (pair of columns)
+  SMO_HD static void product(const cplx* Gs, const double* U, int fo, int pp, int n, double& e0, double& e1) {
+    const int cc = (fo >= 3) ? fo - 3 : fo;
+    const int c1 = (cc + 1) % 3, c2 = (cc + 2) % 3;
+    cplx a1, a2, b1, b2;
+    if (MODE == X_FWD) {
+      a1 = su_pair(U, c1, n, pp); a2 = su_pair(U, c2, n, pp);          // E = U x B
+      b1 = Gs[(c1 * M + n) * HP + pp]; b2 = Gs[(c2 * M + n) * HP + pp];
+    } else {
+      a1 = Gs[(c1 * M + n) * HP + pp]; a2 = Gs[(c2 * M + n) * HP + pp];  // W x U (fo < 3), W x B_f (fo >= 3)
+      if (fo < 3) { b1 = su_pair(U, c1, n, pp); b2 = su_pair(U, c2, n, pp); }
+      else { b1 = Gs[((3 + c1) * M + n) * HP + pp]; b2 = Gs[((3 + c2) * M + n) * HP + pp]; }
+    }
+    e0 = a1.x * b2.x - a2.x * b1.x;
+    e1 = a1.y * b2.y - a2.y * b1.y;
+  }
+
+  template <int PH>
+  SMO_HD static void phase2(const Params& p, int work, int /*step*/, const Ctx& c, State& st) {
+    cplx* S = sin_buf(c.smem);
+    cplx* X = x_buf(c.smem);
+    const double* U = su_buf(c.smem);
+    int f, pp, jj;
+    decode(c.tid, f, pp, jj);
+    const int q = f * HP + pp;
+    const bool more = work + c.ncta < p.nwork;
+    if (PH == 0) {
+      if (st.it == 0) {
+        load_sin(p, work, c); cp_async_commit();
+        load_su(p, work, c); cp_async_commit();
+      }
+      cp_async_wait<1>();                       // the spectral tile of this work item has landed
+    }
+    if (PH == 1) {
+      if (f < NFI && jj < R2) {
+        const int j = jj;
+        const cplx* A = S + f * NH * SP + 2 * pp;
+#pragma unroll
+        for (int i = 0; i < R1; ++i) {
+          const int n = j + R2 * i;
+          double zr = 0.0, zi = 0.0;
+          if (n < NH) {
+            const cplx v = A[n * SP], w = A[n * SP + 1];
+            if (n == 0) { zr = v.x; zi = w.x; } else { zr = v.x - w.y; zi = v.y + w.x; }
+          } else if (n > M - NH) {
+            const int m = M - n;
+            const cplx v = A[m * SP], w = A[m * SP + 1];
+            zr = v.x + w.y; zi = w.x - v.y;
+          }
+          st.re[i] = zr; st.im[i] = zi;
+        }
+        RegFFT<R1, +1>::run(as_arr<R1>(st.re), as_arr<R1>(st.im));
+        const cplx* W = tw1(c.smem) + j;
+#pragma unroll
+        for (int k1 = 1; k1 < R1; ++k1) {
+          const cplx w = W[k1 * R2];
+          const double a = st.re[k1], b = st.im[k1];
+          st.re[k1] = a * w.x + b * w.y;        // multiply by conj(w): inverse direction
+          st.im[k1] = b * w.x - a * w.y;
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) X[(j * F::SK + k1) * NJ + q] = make_double2(st.re[k1], st.im[k1]);
+      }
+    }
+    if (PH == 2) {
+      if (more) load_sin(p, work + c.ncta, c);   // the spectral buffer was consumed in phase 1
+      cp_async_commit();
+      if (f < NFI && jj < R1) {
+        const int k1 = jj;
+#pragma unroll
+        for (int j = 0; j < R2; ++j) {
+          const cplx v = X[(j * F::SK + k1) * NJ + q];
+          st.re[j] = v.x; st.im[j] = v.y;
+        }
+        stage2<F, +1>(st.re, st.im);
+      }
+    }
+    if (PH == 3) {
+      if (f < NFI && jj < R1) {
+        const int k1 = jj;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) X[(f * M + k1 + R1 * k2) * HP + pp] = make_double2(st.re[k2], st.im[k2]);
+      }
+      cp_async_wait<1>();                       // the velocity tile of this work item has landed
+    }
+    if (PH == 4) {
+      if (f < NFO && jj < R1) {
+        const int j = jj;   // stage-1 thread of the swapped factorisation owns rows j + R1*i
+#pragma unroll
+        for (int i = 0; i < R2; ++i) product(X, U, f, pp, j + R1 * i, st.re[i], st.im[i]);
+        RegFFT<R2, -1>::run(as_arr<R2>(st.re), as_arr<R2>(st.im));
+        const cplx* W = tw2(c.smem) + j;
+#pragma unroll
+        for (int k1 = 1; k1 < R2; ++k1) {
+          const cplx w = W[k1 * R1];
+          const double a = st.re[k1], b = st.im[k1];
+          st.re[k1] = a * w.x - b * w.y;
+          st.im[k1] = a * w.y + b * w.x;
+        }
+      }
+    }
+    if (PH == 5) {
+      if (more) load_su(p, work + c.ncta, c);    // the velocity buffer was consumed in phase 4
+      cp_async_commit();
+      if (f < NFO && jj < R1) {
+#pragma unroll
+        for (int k1 = 0; k1 < R2; ++k1) X[(jj * FS::SK + k1) * NJ + q] = make_double2(st.re[k1], st.im[k1]);
+      }
+    }
+    if (PH == 6) {
+      if (f < NFO && jj < R2) {
+        const int k1 = jj;
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+          const cplx v = X[(j * FS::SK + k1) * NJ + q];
+          st.re[j] = v.x; st.im[j] = v.y;
+        }
+        stage2<FS, -1>(st.re, st.im);
+      }
+    }
+    if (PH == 7) {
+      if (f < NFO && jj < R2) {
+#pragma unroll
+        for (int k2 = 0; k2 < R1; ++k2) X[(jj + R2 * k2) * NJ + q] = make_double2(st.re[k2], st.im[k2]);
+      }
+    }
+    if (PH == 8) {
+      if (f < NFO) {
+        cplx* O = p.sout[f] + tile_of(p, work) * T + 2 * pp;
+        const double h = 0.5 * p.scale;
+        for (int k = jj; k < NH; k += RT) {
+          const cplx zk = X[k * NJ + q];
+          const cplx zm = X[((M - k) % M) * NJ + q];
+          O[(long long)k * p.ncols] = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
+          O[(long long)k * p.ncols + 1] = make_double2(h * (zk.y + zm.y), h * (zm.x - zk.x));
+        }
+      }
+      st.it++;
+    }
+  }
+};
+
+// one-off re-layout of the velocity field: grid [3][M][ncols] -> tile-major [ncols/4][3][M][4]
+struct UTileParams {
+  const double* in[3];
+  double* out;
+  int nwork, nsteps;
+  long long ncols;
+  int M;
+};
+struct UTile {
+  typedef UTileParams Params;
+  static constexpr int THREADS = 256;
+  static constexpr int NPHASES = 1;
+  static constexpr int MIN_BLOCKS = 1;
+  static constexpr size_t SMEM = 0;
+  struct State {};
+  template <int PH> SMO_HD static void phase(const Params& p, int work, int, int tid, unsigned char*, State&) {
+    // work item = (row n, block of 256 columns)
+    const long long per_row = (p.ncols + THREADS - 1) / THREADS;
+    const int n = (int)(work / per_row);
+    const long long col = (work % per_row) * THREADS + tid;
+    if (col >= p.ncols) return;
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      p.out[(((col / 4) * 3 + cc) * p.M + n) * 4 + (col % 4)] = p.in[cc][(long long)n * p.ncols + col];
+  }
+};
+
 }  // namespace smo
