@@ -111,7 +111,7 @@ int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef_dev, double* grid_dev, void
 int smo_kdyn_profile_set(smo_kdyn_t* h, int which);
 int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long* launches);
 /* tuning: number of z chunks of the y-pass -> fused x-pass -> y-pass sequence of a forward / adjoint step (keeps the
- * y-padded arrays L2 resident); -1 = choose from the problem size (default), 1 = off */
+ * y-padded arrays L2 resident); -1 = choose from the problem size, 1 = off (default) */
 int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);

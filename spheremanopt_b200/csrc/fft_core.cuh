@@ -56,6 +56,25 @@ template <class F, int DIR> SMO_HD void stage2(double* xr, double* xi) {
   RegFFT<F::R2, DIR>::run(as_arr<F::R2>(xr), as_arr<F::R2>(xi));
 }
 
+// x[k] *= (wr + i*wi)^k for k = 1..R-1, the powers generated on the fly by two interleaved recurrences (odd / even
+// exponents) instead of being loaded: the fused x passes are bound by shared-memory bandwidth, the fp64 pipe has room.
+template <int R> SMO_HD void twiddle_powers(double* xr, double* xi, double wr, double wi) {
+  const double w2r = wr * wr - wi * wi, w2i = 2.0 * wr * wi;
+  double or_ = wr, oi = wi;      // odd exponents: w, w^3, ...
+  double er = w2r, ei = w2i;     // even exponents: w^2, w^4, ...
+#pragma unroll
+  for (int k = 1; k < R; ++k) {
+    const double a = xr[k], b = xi[k];
+    if (k & 1) {
+      xr[k] = a * or_ - b * oi; xi[k] = a * oi + b * or_;
+      const double t = or_ * w2r - oi * w2i; oi = or_ * w2i + oi * w2r; or_ = t;
+    } else {
+      xr[k] = a * er - b * ei; xi[k] = a * ei + b * er;
+      const double t = er * w2r - ei * w2i; ei = er * w2i + ei * w2r; er = t;
+    }
+  }
+}
+
 // position of FFT index n inside a compact array of the 2*kmax+1 retained modes [0..kmax, -kmax..-1]; -1 if dropped
 SMO_HD int compact_index(int n, int M, int kmax) {
   if (n <= kmax) return n;

@@ -627,7 +627,7 @@ template <int M> struct KdOps {
     XFParams p; xffill(p, h, TX, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
     prof_begin(h, PK_X, st);
-    int rc = launch<XFused<F, TX, X_FWD, 3, 3>>(p, st);
+    int rc = launch<XFused<F, TX, X_FWD, 3, 3, (TX == 4)>>(p, st);
     prof_end(h, PK_X, st);
     return rc;
   }
@@ -635,7 +635,7 @@ template <int M> struct KdOps {
     XFParams p; xffill(p, h, TXA, z0, nzc);
     for (int f = 0; f < 6; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
     prof_begin(h, PK_XA, st);
-    int rc = launch<XFused<F, TXA, X_ADJ, 6, 6>>(p, st);
+    int rc = launch<XFused<F, TXA, X_ADJ, 6, 6, (TXA == 4)>>(p, st);
     prof_end(h, PK_XA, st);
     return rc;
   }
@@ -826,7 +826,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->comm = comm;
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
-  h->chunks_fwd = h->chunks_adj = -1;   // -1: choose from the problem size
+  h->chunks_fwd = h->chunks_adj = 1;    // off by default (measured slower at 128^3: the passes are not HBM-bound enough to gain)
   h->hB = h->hU = h->hGB = h->hGU = nullptr; h->snaps = nullptr; h->cap_snap = 0;
   h->tw = nullptr; h->gwork = nullptr; h->vwork = nullptr;
   for (int f = 0; f < MAXF; ++f) h->p1[f] = h->p1t[f] = h->p2[f] = h->cw[f] = nullptr;

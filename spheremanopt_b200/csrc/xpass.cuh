@@ -226,7 +226,7 @@ struct XFParams {
   const cplx* tw;
 };
 
-template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
+template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused {
   typedef XFParams Params;
   typedef typename F::Swapped FS;
   static constexpr bool V2 = true;
@@ -238,29 +238,35 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
   static constexpr int NPHASES = 9;
   static constexpr int MIN_BLOCKS = SMO_X_MB;
   static constexpr int XLEN = (F::XP > FS::XP) ? ((F::XP > M) ? F::XP : M) : ((FS::XP > M) ? FS::XP : M);
-  static constexpr int SP = T_ + 1;                  // pitch of a spectral row in shared memory (bank spread)
+  // Thread order and shared-memory layouts are chosen so that every quarter-warp access is bank-conflict free:
+  //   JFAST = false (T = 8): lanes run over the HP = 4 column pairs, then over the stage threads;  X is [e][NJ]
+  //   JFAST = true  (T = 4): lanes run over the RT stage threads, then over the HP = 2 pairs;      X is [q][XLP]
+  static constexpr int XLP = XLEN + 4;               // q pitch of the JFAST exchange layout (= 4 mod 8)
+  static constexpr int SP = T_ + 1;                  // pitch of a spectral row in shared memory (odd: bank spread)
   static constexpr int SIN_ELEMS = NFI * NH * SP;    // cplx
-  static constexpr int SU_DOUBLES = 3 * M * T_;
-  static constexpr int X_ELEMS = NJ * XLEN;
-  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + X_ELEMS + 2 * M) * sizeof(cplx) + (size_t)SU_DOUBLES * sizeof(double);
+  static constexpr int UB = 3 * M * 4 + 8;           // doubles per 4-column velocity block in shared memory (padded)
+  static constexpr int SU_DOUBLES = TB * UB;
+  static constexpr int X_ELEMS = JFAST ? NJ * XLP : NJ * XLEN;
+  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + X_ELEMS) * sizeof(cplx) + (size_t)SU_DOUBLES * sizeof(double);
   static_assert(T_ % 4 == 0, "column tiles are multiples of the 4-column velocity blocks");
   static_assert(MODE == X_FWD || MODE == X_ADJ, "fused modes only");
+  static_assert(!JFAST || T_ == 4, "the JFAST layouts assume one velocity block per tile");
   struct State {
     double re[RT], im[RT];
+    double wr, wi;     // w_M^jj = exp(-2 pi i jj / M): base of this thread's inter-stage twiddles
     int it;
   };
 
   SMO_HD static cplx* sin_buf(unsigned char* s) { return reinterpret_cast<cplx*>(s); }
   SMO_HD static cplx* x_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
-  SMO_HD static cplx* tw1(unsigned char* s) { return x_buf(s) + X_ELEMS; }        // inverse stage twiddles [k1][j]  (R1 x R2)
-  SMO_HD static cplx* tw2(unsigned char* s) { return tw1(s) + M; }               // forward (swapped) stage twiddles [k1][j]  (R2 x R1)
-  SMO_HD static double* su_buf(unsigned char* s) { return reinterpret_cast<double*>(tw2(s) + M); }
+  SMO_HD static double* su_buf(unsigned char* s) { return reinterpret_cast<double*>(x_buf(s) + X_ELEMS); }
 
   SMO_HD static void decode(int tid, int& f, int& pp, int& jj) {
-    pp = tid % HP;
-    jj = (tid / HP) % RT;
+    if (JFAST) { jj = tid % RT; pp = (tid / RT) % HP; } else { pp = tid % HP; jj = (tid / HP) % RT; }
     f = tid / (HP * RT);
   }
+  SMO_HD static int xe(int e, int q) { return JFAST ? q * XLP + e : e * NJ + q; }                 // exchange / spectrum
+  SMO_HD static int gi(int f, int n, int pp) { return JFAST ? (f * HP + pp) * M + n : (f * M + n) * HP + pp; }   // grid values
   SMO_HD static long long tile_of(const Params& p, int work) {
     return (long long)(work / p.tiles_per_row) * p.row_tiles + p.tile0 + (work % p.tiles_per_row);
   }
@@ -268,8 +274,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
   SMO_HD static void load_sin(const Params& p, int work, const Ctx& c) {
     cplx* S = sin_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
-    // chunks: (f, row, tcol); lanes run over tcol fastest
-    for (int q = c.tid; q < NFI * NH * T; q += THREADS) {
+    for (int q = c.tid; q < NFI * NH * T; q += THREADS) {     // chunks (f, row, column), column fastest
       const int tc = q % T, r = q / T;
       const int row = r % NH, f = r / NH;
       cp_async16(&S[(f * NH + row) * SP + tc], p.sin[f] + (long long)row * p.ncols + col0 + tc);
@@ -278,22 +283,27 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
   SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
     double* U = su_buf(c.smem);
     const double* src = p.ut + tile_of(p, work) * TB * (3LL * M * 4);
-    for (int q = c.tid; q < SU_DOUBLES / 2; q += THREADS) cp_async16(&U[2 * q], src + 2 * q);
+    constexpr int CH = 3 * M * 2;                              // 16-byte chunks per 4-column block
+    for (int q = c.tid; q < TB * CH; q += THREADS) {
+      const int b = q / CH, r = q % CH;
+      if (JFAST) {   // [c][pair][n] : chunk r = (c*M + n)*2 + pair
+        cp_async16(&U[2 * (((r / 2) / M * 2 + (r % 2)) * M + (r / 2) % M)], src + 2 * q);
+      } else {       // [block][c][n][4], block pitch UB
+        cp_async16(&U[b * UB + 2 * r], src + 2 * q);
+      }
+    }
   }
   // velocity pair (columns 2pp, 2pp+1 of the tile) of component cidx at grid row n
   SMO_HD static cplx su_pair(const double* U, int cidx, int n, int pp) {
-    const int blk = pp / 2, w = (pp % 2) * 2;
-    const double* q = U + ((blk * 3 + cidx) * M + n) * 4 + w;
+    const double* q = JFAST ? U + 2 * ((cidx * 2 + pp) * M + n) : U + (pp / 2) * UB + ((cidx * M + n) * 4 + (pp % 2) * 2);
     return make_double2(q[0], q[1]);
   }
 
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
-    cplx* W1 = tw1(c.smem);
-    cplx* W2 = tw2(c.smem);
-    for (int m = c.tid; m < M; m += THREADS) {
-      W1[m] = ldg_c(p.tw + ((m % R2) * (m / R2)) % M);   // [k1 < R1][j < R2]
-      W2[m] = ldg_c(p.tw + ((m % R1) * (m / R1)) % M);   // [k1 < R2][j < R1]
-    }
+    int f, pp, jj;
+    decode(c.tid, f, pp, jj);
+    const cplx w = ldg_c(p.tw + jj);
+    st.wr = w.x; st.wi = w.y;
     st.it = 0;
   }
 
@@ -304,11 +314,11 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
     cplx a1, a2, b1, b2;
     if (MODE == X_FWD) {
       a1 = su_pair(U, c1, n, pp); a2 = su_pair(U, c2, n, pp);          // E = U x B
-      b1 = Gs[(c1 * M + n) * HP + pp]; b2 = Gs[(c2 * M + n) * HP + pp];
+      b1 = Gs[gi(c1, n, pp)]; b2 = Gs[gi(c2, n, pp)];
     } else {
-      a1 = Gs[(c1 * M + n) * HP + pp]; a2 = Gs[(c2 * M + n) * HP + pp];  // W x U (fo < 3), W x B_f (fo >= 3)
+      a1 = Gs[gi(c1, n, pp)]; a2 = Gs[gi(c2, n, pp)];                  // W x U (fo < 3), W x B_f (fo >= 3)
       if (fo < 3) { b1 = su_pair(U, c1, n, pp); b2 = su_pair(U, c2, n, pp); }
-      else { b1 = Gs[((3 + c1) * M + n) * HP + pp]; b2 = Gs[((3 + c2) * M + n) * HP + pp]; }
+      else { b1 = Gs[gi(3 + c1, n, pp)]; b2 = Gs[gi(3 + c2, n, pp)]; }
     }
     e0 = a1.x * b2.x - a2.x * b1.x;
     e1 = a1.y * b2.y - a2.y * b1.y;
@@ -349,16 +359,9 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
           st.re[i] = zr; st.im[i] = zi;
         }
         RegFFT<R1, +1>::run(as_arr<R1>(st.re), as_arr<R1>(st.im));
-        const cplx* W = tw1(c.smem) + j;
+        twiddle_powers<R1>(st.re, st.im, st.wr, -st.wi);      // conj: inverse direction
 #pragma unroll
-        for (int k1 = 1; k1 < R1; ++k1) {
-          const cplx w = W[k1 * R2];
-          const double a = st.re[k1], b = st.im[k1];
-          st.re[k1] = a * w.x + b * w.y;        // multiply by conj(w): inverse direction
-          st.im[k1] = b * w.x - a * w.y;
-        }
-#pragma unroll
-        for (int k1 = 0; k1 < R1; ++k1) X[(j * F::SK + k1) * NJ + q] = make_double2(st.re[k1], st.im[k1]);
+        for (int k1 = 0; k1 < R1; ++k1) X[xe(j * F::SK + k1, q)] = make_double2(st.re[k1], st.im[k1]);
       }
     }
     if (PH == 2) {
@@ -368,7 +371,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
         const int k1 = jj;
 #pragma unroll
         for (int j = 0; j < R2; ++j) {
-          const cplx v = X[(j * F::SK + k1) * NJ + q];
+          const cplx v = X[xe(j * F::SK + k1, q)];
           st.re[j] = v.x; st.im[j] = v.y;
         }
         stage2<F, +1>(st.re, st.im);
@@ -378,7 +381,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
       if (f < NFI && jj < R1) {
         const int k1 = jj;
 #pragma unroll
-        for (int k2 = 0; k2 < R2; ++k2) X[(f * M + k1 + R1 * k2) * HP + pp] = make_double2(st.re[k2], st.im[k2]);
+        for (int k2 = 0; k2 < R2; ++k2) X[gi(f, k1 + R1 * k2, pp)] = make_double2(st.re[k2], st.im[k2]);
       }
       cp_async_wait<1>();                       // the velocity tile of this work item has landed
     }
@@ -388,14 +391,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
 #pragma unroll
         for (int i = 0; i < R2; ++i) product(X, U, f, pp, j + R1 * i, st.re[i], st.im[i]);
         RegFFT<R2, -1>::run(as_arr<R2>(st.re), as_arr<R2>(st.im));
-        const cplx* W = tw2(c.smem) + j;
-#pragma unroll
-        for (int k1 = 1; k1 < R2; ++k1) {
-          const cplx w = W[k1 * R1];
-          const double a = st.re[k1], b = st.im[k1];
-          st.re[k1] = a * w.x - b * w.y;
-          st.im[k1] = a * w.y + b * w.x;
-        }
+        twiddle_powers<R2>(st.re, st.im, st.wr, st.wi);
       }
     }
     if (PH == 5) {
@@ -403,7 +399,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
       cp_async_commit();
       if (f < NFO && jj < R1) {
 #pragma unroll
-        for (int k1 = 0; k1 < R2; ++k1) X[(jj * FS::SK + k1) * NJ + q] = make_double2(st.re[k1], st.im[k1]);
+        for (int k1 = 0; k1 < R2; ++k1) X[xe(jj * FS::SK + k1, q)] = make_double2(st.re[k1], st.im[k1]);
       }
     }
     if (PH == 6) {
@@ -411,7 +407,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
         const int k1 = jj;
 #pragma unroll
         for (int j = 0; j < R1; ++j) {
-          const cplx v = X[(j * FS::SK + k1) * NJ + q];
+          const cplx v = X[xe(j * FS::SK + k1, q)];
           st.re[j] = v.x; st.im[j] = v.y;
         }
         stage2<FS, -1>(st.re, st.im);
@@ -420,16 +416,21 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XFused {
     if (PH == 7) {
       if (f < NFO && jj < R2) {
 #pragma unroll
-        for (int k2 = 0; k2 < R1; ++k2) X[(jj + R2 * k2) * NJ + q] = make_double2(st.re[k2], st.im[k2]);
+        for (int k2 = 0; k2 < R1; ++k2) {
+          const int k = jj + R2 * k2;   // only the retained modes and their mirror images are needed by phase 8
+          if (k < NH || k > M - NH) X[xe(k, q)] = make_double2(st.re[k2], st.im[k2]);
+        }
       }
     }
     if (PH == 8) {
-      if (f < NFO) {
-        cplx* O = p.sout[f] + tile_of(p, work) * T + 2 * pp;
+      // own thread order (column pairs fastest) so that a row's T columns are stored by adjacent lanes
+      const int pp8 = c.tid % HP, kk = (c.tid / HP) % RT, f8 = c.tid / (HP * RT), q8 = f8 * HP + pp8;
+      if (f8 < NFO) {
+        cplx* O = p.sout[f8] + tile_of(p, work) * T + 2 * pp8;
         const double h = 0.5 * p.scale;
-        for (int k = jj; k < NH; k += RT) {
-          const cplx zk = X[k * NJ + q];
-          const cplx zm = X[((M - k) % M) * NJ + q];
+        for (int k = kk; k < NH; k += RT) {
+          const cplx zk = X[xe(k, q8)];
+          const cplx zm = X[xe((M - k) % M, q8)];
           O[(long long)k * p.ncols] = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
           O[(long long)k * p.ncols + 1] = make_double2(h * (zk.y + zm.y), h * (zm.x - zk.x));
         }

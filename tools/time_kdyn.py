@@ -32,7 +32,7 @@ names = {0: "total", 1: "z-pass", 2: "y-pass", 3: "x-fwd", 4: "epilogue", 5: "a2
 C_ = (N // 2) * (N - 1) ** 2 * 16; P1 = (N // 2) * (N - 1) * M * 16; P2 = (N // 2) * M * M * 16
 alg_f = 9 * C_ + 12 * P1 + 15 * P2; alg_a = 18 * C_ + 24 * P1 + 27 * P2
 import os
-chunk_sets = [tuple(int(v) for v in cs.split(",")) for cs in os.environ.get("CHUNKS", "-1,-1").split(";")]
+chunk_sets = [tuple(int(v) for v in cs.split(",")) for cs in os.environ.get("CHUNKS", "1,1").split(";")]
 kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)   # warm-up (lazy module loading)
 for cf, ca in chunk_sets:
   lib.smo_kdyn_set_chunks(dom.h, cf, ca)
