@@ -91,6 +91,9 @@ SMO_HD int imin(int a, int b) { return a < b ? a : b; }
 template <class K, class = void> struct is_v2 { static constexpr bool value = false; };
 template <class K> struct is_v2<K, decltype((void)K::V2)> { static constexpr bool value = K::V2; };
 
+template <class K, class = void> struct has_sync_kinds { static constexpr bool value = false; };
+template <class K> struct has_sync_kinds<K, decltype((void)K::sync_after(0))> { static constexpr bool value = true; };
+
 #if !defined(SMO_EMUL)
 template <class K, int PH, bool END> struct PhaseStep;
 template <class K, int PH> struct PhaseStep<K, PH, false> {
@@ -102,7 +105,13 @@ template <class K, int PH> struct PhaseStep<K, PH, false> {
     } else {
       K::template phase<PH>(p, work, step, tid, smem, st);
     }
-    __syncthreads();
+    // barrier after the phase: CTA-wide by default; kernels may declare `sync_after(PH)` = 0 none, 1 warp, 2 CTA
+    if constexpr (has_sync_kinds<K>::value) {
+      if constexpr (K::sync_after(PH) == 2) __syncthreads();
+      else if constexpr (K::sync_after(PH) == 1) __syncwarp();
+    } else {
+      __syncthreads();
+    }
     PhaseStep<K, PH + 1, (PH + 1 >= K::NPHASES)>::run(p, work, step, tid, smem, st);
   }
 };
@@ -114,7 +123,7 @@ template <class K, int PH> struct PhaseStep<K, PH, true> {
 // One CTA loops over work items blockIdx.x, blockIdx.x + gridDim.x, ... (persistent-style grid).
 template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const typename K::Params p) {
-  extern __shared__ __align__(16) unsigned char smo_smem[];
+  extern __shared__ __align__(128) unsigned char smo_smem[];
   typename K::State st;
   if constexpr (is_v2<K>::value) {
     Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
@@ -148,9 +157,9 @@ template <class K, int PH> struct EmulStep<K, PH, true> {
 };
 // Host emulation of smo_kernel<K>: CTAs run one after another, threads of a CTA phase by phase.
 template <class K> void emul_kernel(int grid, size_t smem_bytes, const typename K::Params& p) {
-  std::vector<unsigned char> smem(smem_bytes + 64);
+  std::vector<unsigned char> smem(smem_bytes + 256);
   unsigned char* sm = smem.data();
-  sm += (16 - ((uintptr_t)sm & 15)) & 15;
+  sm += (128 - ((uintptr_t)sm & 127)) & 127;
   std::vector<typename K::State> st(K::THREADS);
   for (int cta = 0; cta < grid; ++cta) {
     g_emul_cta = cta; g_emul_ncta = grid;

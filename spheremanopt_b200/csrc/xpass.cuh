@@ -242,15 +242,21 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
   //   JFAST = false (T = 8): lanes run over the HP = 4 column pairs, then over the stage threads;  X is [e][NJ]
   //   JFAST = true  (T = 4): lanes run over the RT stage threads, then over the HP = 2 pairs;      X is [q][XLP]
   static constexpr int XLP = XLEN + 4;               // q pitch of the JFAST exchange layout (= 4 mod 8)
-  static constexpr int SP = T_ + 1;                  // pitch of a spectral row in shared memory (odd: bank spread)
-  static constexpr int SIN_ELEMS = NFI * NH * SP;    // cplx
-  static constexpr int UB = 3 * M * 4 + 8;           // doubles per 4-column velocity block in shared memory (padded)
-  static constexpr int SU_DOUBLES = TB * UB;
+  // The cp.async targets (spectral tile, velocity tile) are dense 128-byte lines with an XOR swizzle inside each
+  // line instead of padded pitches: LDGSTS writes a line in one wavefront only when 8 lanes cover one ALIGNED line
+  // (measured: padded / scattered targets cost 8-32 wavefronts per instruction), and the swizzle keeps the reads
+  // of the transform phases conflict free.
+  static constexpr int SIN_ELEMS = NFI * NH * T_;    // cplx (16-byte units)
+  static constexpr int UBU = 3 * M * 2;              // 16-byte units per 4-column velocity block
+  static constexpr int SU_UNITS = TB * UBU;
   static constexpr int X_ELEMS = JFAST ? NJ * XLP : NJ * XLEN;
-  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + X_ELEMS) * sizeof(cplx) + (size_t)SU_DOUBLES * sizeof(double);
+  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS) * sizeof(cplx);
+  static_assert(SIN_ELEMS % 8 == 0 && SU_UNITS % 8 == 0, "cp.async regions must be whole 128-byte lines");
   static_assert(T_ % 4 == 0, "column tiles are multiples of the 4-column velocity blocks");
   static_assert(MODE == X_FWD || MODE == X_ADJ, "fused modes only");
-  static_assert(!JFAST || T_ == 4, "the JFAST layouts assume one velocity block per tile");
+  static_assert(JFAST == (T_ == 4), "T = 4 uses the stage-thread-fastest order, T = 8 the pair-fastest order");
+  static_assert(T_ == 4 || T_ == 8, "supported column tiles");
+  static_assert(NH % 2 == 0, "two spectral rows per 128-byte line need an even number of retained modes");
   struct State {
     double re[RT], im[RT];
     double wr, wi;     // w_M^jj = exp(-2 pi i jj / M): base of this thread's inter-stage twiddles
@@ -258,8 +264,18 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
   };
 
   SMO_HD static cplx* sin_buf(unsigned char* s) { return reinterpret_cast<cplx*>(s); }
-  SMO_HD static cplx* x_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
-  SMO_HD static double* su_buf(unsigned char* s) { return reinterpret_cast<double*>(x_buf(s) + X_ELEMS); }
+  SMO_HD static cplx* su_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
+  SMO_HD static cplx* x_buf(unsigned char* s) { return su_buf(s) + SU_UNITS; }
+  // unit index of spectral entry (field f, row, tile column col)
+  SMO_HD static int si(int f, int row, int col) {
+    if (T == 8) return (f * NH + row) * 8 + (col ^ (row & 7));
+    return (((f * NH + row) >> 1) << 3) + ((((row & 1) << 2) + col) ^ ((row >> 1) & 3));   // T == 4: two rows per line
+  }
+  // unit index of the velocity pair (component cidx, grid row n, column pair pp)
+  SMO_HD static int ui(int cidx, int n, int pp) {
+    if (JFAST) return ((cidx * M + n) * 2 + pp) ^ ((n >> 2) & 1);                            // [c][n][pair], one block
+    return ((pp >> 1) * UBU + (cidx * M + n) * 2 + (pp & 1)) ^ (((pp >> 1) & 1) << 2);      // [block][c][n][half]
+  }
 
   SMO_HD static void decode(int tid, int& f, int& pp, int& jj) {
     if (JFAST) { jj = tid % RT; pp = (tid / RT) % HP; } else { pp = tid % HP; jj = (tid / HP) % RT; }
@@ -277,27 +293,19 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
     for (int q = c.tid; q < NFI * NH * T; q += THREADS) {     // chunks (f, row, column), column fastest
       const int tc = q % T, r = q / T;
       const int row = r % NH, f = r / NH;
-      cp_async16(&S[(f * NH + row) * SP + tc], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+      cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
     }
   }
   SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
-    double* U = su_buf(c.smem);
+    cplx* U = su_buf(c.smem);
     const double* src = p.ut + tile_of(p, work) * TB * (3LL * M * 4);
-    constexpr int CH = 3 * M * 2;                              // 16-byte chunks per 4-column block
-    for (int q = c.tid; q < TB * CH; q += THREADS) {
-      const int b = q / CH, r = q % CH;
-      if (JFAST) {   // [c][pair][n] : chunk r = (c*M + n)*2 + pair
-        cp_async16(&U[2 * (((r / 2) / M * 2 + (r % 2)) * M + (r / 2) % M)], src + 2 * q);
-      } else {       // [block][c][n][4], block pitch UB
-        cp_async16(&U[b * UB + 2 * r], src + 2 * q);
-      }
+    for (int q = c.tid; q < SU_UNITS; q += THREADS) {          // gmem chunk q = (block, component, row, half)
+      const int b = q / UBU, r = q % UBU;
+      cp_async16(&U[ui(r / (2 * M), (r / 2) % M, b * 2 + (r & 1))], src + 2 * q);
     }
   }
   // velocity pair (columns 2pp, 2pp+1 of the tile) of component cidx at grid row n
-  SMO_HD static cplx su_pair(const double* U, int cidx, int n, int pp) {
-    const double* q = JFAST ? U + 2 * ((cidx * 2 + pp) * M + n) : U + (pp / 2) * UB + ((cidx * M + n) * 4 + (pp % 2) * 2);
-    return make_double2(q[0], q[1]);
-  }
+  SMO_HD static cplx su_pair(const cplx* U, int cidx, int n, int pp) { return U[ui(cidx, n, pp)]; }
 
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
     int f, pp, jj;
@@ -308,7 +316,7 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
   }
 
   // product needed by output field fo at grid row n (pair of columns)
-  SMO_HD static void product(const cplx* Gs, const double* U, int fo, int pp, int n, double& e0, double& e1) {
+  SMO_HD static void product(const cplx* Gs, const cplx* U, int fo, int pp, int n, double& e0, double& e1) {
     const int cc = (fo >= 3) ? fo - 3 : fo;
     const int c1 = (cc + 1) % 3, c2 = (cc + 2) % 3;
     cplx a1, a2, b1, b2;
@@ -328,7 +336,7 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
   SMO_HD static void phase2(const Params& p, int work, int /*step*/, const Ctx& c, State& st) {
     cplx* S = sin_buf(c.smem);
     cplx* X = x_buf(c.smem);
-    const double* U = su_buf(c.smem);
+    const cplx* U = su_buf(c.smem);
     int f, pp, jj;
     decode(c.tid, f, pp, jj);
     const int q = f * HP + pp;
@@ -343,17 +351,16 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
     if (PH == 1) {
       if (f < NFI && jj < R2) {
         const int j = jj;
-        const cplx* A = S + f * NH * SP + 2 * pp;
 #pragma unroll
         for (int i = 0; i < R1; ++i) {
           const int n = j + R2 * i;
           double zr = 0.0, zi = 0.0;
           if (n < NH) {
-            const cplx v = A[n * SP], w = A[n * SP + 1];
+            const cplx v = S[si(f, n, 2 * pp)], w = S[si(f, n, 2 * pp + 1)];
             if (n == 0) { zr = v.x; zi = w.x; } else { zr = v.x - w.y; zi = v.y + w.x; }
           } else if (n > M - NH) {
             const int m = M - n;
-            const cplx v = A[m * SP], w = A[m * SP + 1];
+            const cplx v = S[si(f, m, 2 * pp)], w = S[si(f, m, 2 * pp + 1)];
             zr = v.x + w.y; zi = w.x - v.y;
           }
           st.re[i] = zr; st.im[i] = zi;
