@@ -110,6 +110,13 @@ int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef_dev, double* grid_dev, void
  * smo_kdyn_profile_read returns the accumulated CUDA-event time (ms) and launch count since the last set. */
 int smo_kdyn_profile_set(smo_kdyn_t* h, int which);
 int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long* launches);
+/* Peer-memory transposes (replaces the all-to-all by stores over NVLink fused into the FFT passes).  Every rank
+ * calls smo_kdyn_peer_export (writes smo_kdyn_peer_handle_bytes() bytes of CUDA IPC handles), the host program
+ * all-gathers the blobs in rank order and every rank calls smo_kdyn_peer_attach with the concatenation.  Without
+ * attachment a multi-rank handle uses grouped ncclSend/ncclRecv. */
+int smo_kdyn_peer_handle_bytes(void);
+int smo_kdyn_peer_export(smo_kdyn_t* h, void* handles_out);
+int smo_kdyn_peer_attach(smo_kdyn_t* h, const void* all_handles);
 /* tuning: number of z chunks of the y-pass -> fused x-pass -> y-pass sequence of a forward / adjoint step (keeps the
  * y-padded arrays L2 resident); -1 = choose from the problem size, 1 = off (default) */
 int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);

@@ -48,6 +48,9 @@ SIGNATURES = {
     "smo_kdyn_to_grid": (i32, [vp, vp, dp, vp]),
     "smo_kdyn_profile_set": (i32, [vp, i32]),
     "smo_kdyn_profile_read": (i32, [vp, C.POINTER(f64), C.POINTER(ll)]),
+    "smo_kdyn_peer_handle_bytes": (i32, []),
+    "smo_kdyn_peer_export": (i32, [vp, vp]),
+    "smo_kdyn_peer_attach": (i32, [vp, vp]),
     "smo_kdyn_set_chunks": (i32, [vp, i32, i32]),
     "smo_kdyn_use_graph": (i32, [vp, i32]),
     # communicator (multi-GPU slab decomposition)

@@ -41,6 +41,13 @@ struct PassParams {
   int kmax;
   double scale;             // applied to outputs
   const cplx* tw;           // exp(-2 pi i m / M), m < M
+  // Transposes fused into the stores (multi-GPU slab decomposition): results are written straight into the peers'
+  // buffers over NVLink instead of a local buffer followed by an all-to-all.
+  //   peer_mode 1 (inverse z pass): full-length index k goes to peer k / seglen, at peer_off + line*seglen + k % seglen
+  //   peer_mode 2 (forward y pass): row a (= kx) goes to peer a / peer_rows, at peer_off + (a % peer_rows)*out_sA + ...
+  int peer_mode, peer_rows;
+  long long peer_off;       // this rank's block inside every peer buffer (rank * blk)
+  cplx* peer_out[MAXF][MAXP];
 };
 
 template <class F, int DIR, bool TFAST, int T_> struct FftPass {
@@ -123,7 +130,8 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
       const int k = jj + R1 * k2;
       int off = -1;
       if (jj < R1) {
-        if (PAD) off = (int)full_off(p, k, p.out_sN);
+        if (PAD && p.peer_mode == 1) off = ((k / p.seglen) << 24) | (k % p.seglen);   // (peer, offset inside the segment)
+        else if (PAD) off = (int)full_off(p, k, p.out_sN);
         else { const int cidx = compact_index(k, M, KMAX); if (cidx >= 0) off = (int)((long long)cidx * p.out_sN); }
       }
       st.ooff[k2] = off;
@@ -188,11 +196,24 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
         decode(p, work, f, a, bt);
         const int b = bt * T + t;
         if (b < p.nB) {
-          cplx* dst = p.out[f] + (long long)a * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
+          if (PAD && !TFAST && p.peer_mode == 1) {
+            const long long line = p.peer_off + (long long)(p.b0 + b) * p.out_sB;
 #pragma unroll
-          for (int k2 = 0; k2 < R2; ++k2) {
-            const int off = st.ooff[k2];
-            if (PAD || off >= 0) dst[off] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
+            for (int k2 = 0; k2 < R2; ++k2) {
+              const int off = st.ooff[k2];
+              p.peer_out[f][off >> 24][line + (off & 0xffffff)] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
+            }
+          } else {
+            cplx* dst;
+            if (!PAD && TFAST && p.peer_mode == 2)
+              dst = p.peer_out[f][a / p.peer_rows] + p.peer_off + (long long)(a % p.peer_rows) * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
+            else
+              dst = p.out[f] + (long long)a * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) {
+              const int off = st.ooff[k2];
+              if (PAD || off >= 0) dst[off] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
+            }
           }
         }
       }

@@ -438,6 +438,10 @@ struct smo_kdyn {
   size_t ev_used;
 #endif
   int use_graph;
+  // peer-memory transposes (CUDA IPC): pointers to every rank's p1 / p1t buffers and flag words
+  int peer_on;
+  cplx* peer_p1[MAXF][MAXP]; cplx* peer_p1t[MAXF][MAXP];
+  unsigned long long* flags; unsigned long long* peer_flags[MAXP]; unsigned long long epoch;
   int chunks_fwd, chunks_adj;   // z-chunked y/x/y sequence (L2-resident P2 arrays); <= 1: whole slab at once
 };
 
@@ -478,9 +482,38 @@ static void prof_collect(smo_kdyn*, rt_stream) {}
 typedef void (*smo_emul_a2a_fn)(const void* send, void* recv, long long bytes_per_peer, void* user);
 struct EmulComm { smo_emul_a2a_fn fn; void* user; };
 #endif
+#if !defined(SMO_EMUL)
+// Cross-GPU barrier of the peer-memory transposes: thread s publishes this rank's epoch in rank s's flag word
+// (after a system-wide fence, so that the remote stores of the preceding pass kernel are visible first) and then
+// waits until rank s has published the same epoch here.  One tiny launch per transpose; every GPU runs its own copy.
+struct PeerFlags { unsigned long long* peer[MAXP]; };
+__global__ void peer_barrier_kernel(PeerFlags pf, volatile unsigned long long* mine, int rank, int nranks, unsigned long long epoch) {
+  const int s = (int)threadIdx.x;
+  if (s < nranks) {
+    __threadfence_system();
+    *((volatile unsigned long long*)(pf.peer[s] + rank)) = epoch;
+    __threadfence_system();
+    while (mine[s] < epoch) { /* spin */ }
+    __threadfence_system();
+  }
+}
+#endif
 static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_stream st) {
   if (h->nranks == 1) return 0;
   const size_t blk = (size_t)h->nkx * h->Nc * h->nz;
+#if !defined(SMO_EMUL)
+  if (h->peer_on) {   // the data already sits in the peers' buffers (stores of the preceding pass): barrier only
+    (void)src; (void)dst; (void)nf; (void)blk;
+    PeerFlags pf;
+    for (int s = 0; s < MAXP; ++s) pf.peer[s] = h->peer_flags[s];
+    h->epoch++;
+    prof_begin(h, PK_A2A, st);
+    peer_barrier_kernel<<<1, 32, 0, st>>>(pf, h->flags, h->rank, h->nranks, h->epoch);
+    g_launches++;
+    prof_end(h, PK_A2A, st);
+    return rt_check("peer barrier launch");
+  }
+#endif
 #if defined(SMO_EMUL)
   EmulComm* c = (EmulComm*)h->comm;
   for (int f = 0; f < nf; ++f) c->fn(src[f], dst[f], (long long)(blk * sizeof(cplx)), c->user);
@@ -540,6 +573,10 @@ template <int M> struct KdOps {
     p.in_sA = 0; p.in_sB = h->Pc;
     p.out_sA = 0; p.out_sB = h->nz;
     if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
+    if (h->peer_on && out == h->p1) {   // fused transpose: segment s is stored straight into rank s's p1t
+      p.peer_mode = 1; p.peer_off = (long long)h->rank * p.blk;
+      for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_out[f][s2] = h->peer_p1t[f][s2];
+    }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Z, st);
     int rc = launch<FftPass<F, +1, false, TZ>>(p, st);
@@ -581,6 +618,10 @@ template <int M> struct KdOps {
     p.in_sA = (long long)M * h->nz; p.in_sB = 1; p.in_sN = h->nz;
     p.out_sA = (long long)h->Nc * h->nz; p.out_sB = 1; p.out_sN = h->nz;
     p.scale = 1.0 / M;
+    if (h->peer_on && out == h->p1t) {   // fused transpose: row kx is stored straight into its owner's p1
+      p.peer_mode = 2; p.peer_rows = h->nkx; p.peer_off = (long long)h->rank * h->nkx * h->Nc * h->nz;
+      for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_out[f][s2] = h->peer_p1[f][s2];
+    }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Y, st);
     int rc = launch<FftPass<F, -1, true, TY>>(p, st);
@@ -826,6 +867,9 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->comm = comm;
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
+  h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
+  for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
+  for (int s2 = 0; s2 < MAXP; ++s2) h->peer_flags[s2] = nullptr;
   h->chunks_fwd = h->chunks_adj = 1;    // off by default (measured slower at 128^3: the passes are not HBM-bound enough to gain)
   h->hB = h->hU = h->hGB = h->hGU = nullptr; h->snaps = nullptr; h->cap_snap = 0;
   h->tw = nullptr; h->gwork = nullptr; h->vwork = nullptr;
@@ -868,6 +912,16 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
   }
   for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); }
   rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut);
+#if !defined(SMO_EMUL)
+  if (h->peer_on) {
+    for (int s = 0; s < h->nranks; ++s) {
+      if (s == h->rank) continue;
+      for (int f = 0; f < MAXF; ++f) { cudaIpcCloseMemHandle(h->peer_p1[f][s]); cudaIpcCloseMemHandle(h->peer_p1t[f][s]); }
+      cudaIpcCloseMemHandle(h->peer_flags[s]);
+    }
+  }
+  rt_free(h->flags);
+#endif
   rt_free(h->hB); rt_free(h->hU); rt_free(h->hGB); rt_free(h->hGU); rt_free(h->snaps);
 #if !defined(SMO_EMUL)
   if (h->ev) { for (cudaEvent_t e : *h->ev) cudaEventDestroy(e); delete h->ev; }
@@ -970,6 +1024,56 @@ extern "C" int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long*
   if (launches) *launches = h->prof_n;
   return 0;
 }
+// ---- peer-memory attachment (CUDA IPC) --------------------------------------------------------------------------
+#if !defined(SMO_EMUL)
+extern "C" int smo_kdyn_peer_handle_bytes(void) { return (int)((2 * MAXF + 1) * sizeof(cudaIpcMemHandle_t)); }
+extern "C" int smo_kdyn_peer_export(smo_kdyn_t* h, void* out) {
+  if (!h || !out) return fail(SMO_E_ARG, "smo_kdyn_peer_export: bad argument");
+  if (h->nranks < 2) return fail(SMO_E_ARG, "smo_kdyn_peer_export: single-rank handle");
+  if (h->nranks > MAXP) return fail(SMO_E_UNSUPPORTED, "peer transposes support at most %d ranks", MAXP);
+  if (!h->flags) {
+    TRY(rt_malloc((void**)&h->flags, sizeof(unsigned long long) * MAXP));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t* hd = (cudaIpcMemHandle_t*)out;
+  for (int f = 0; f < MAXF; ++f) {
+    CUDA_TRY(cudaIpcGetMemHandle(&hd[f], h->p1[f]));
+    CUDA_TRY(cudaIpcGetMemHandle(&hd[MAXF + f], h->p1t[f]));
+  }
+  CUDA_TRY(cudaIpcGetMemHandle(&hd[2 * MAXF], h->flags));
+  return 0;
+}
+extern "C" int smo_kdyn_peer_attach(smo_kdyn_t* h, const void* all) {
+  if (!h || !all) return fail(SMO_E_ARG, "smo_kdyn_peer_attach: bad argument");
+  if (h->nranks < 2 || h->nranks > MAXP || !h->flags) return fail(SMO_E_STATE, "smo_kdyn_peer_attach: export first (2..%d ranks)", MAXP);
+  const cudaIpcMemHandle_t* hd = (const cudaIpcMemHandle_t*)all;
+  const int per = 2 * MAXF + 1;
+  for (int s = 0; s < h->nranks; ++s) {
+    if (s == h->rank) {
+      for (int f = 0; f < MAXF; ++f) { h->peer_p1[f][s] = h->p1[f]; h->peer_p1t[f][s] = h->p1t[f]; }
+      h->peer_flags[s] = h->flags;
+      continue;
+    }
+    for (int f = 0; f < MAXF; ++f) {
+      void* q = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&q, hd[s * per + f], cudaIpcMemLazyEnablePeerAccess));
+      h->peer_p1[f][s] = (cplx*)q;
+      CUDA_TRY(cudaIpcOpenMemHandle(&q, hd[s * per + MAXF + f], cudaIpcMemLazyEnablePeerAccess));
+      h->peer_p1t[f][s] = (cplx*)q;
+    }
+    void* q = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&q, hd[s * per + 2 * MAXF], cudaIpcMemLazyEnablePeerAccess));
+    h->peer_flags[s] = (unsigned long long*)q;
+  }
+  h->peer_on = 1;
+  return 0;
+}
+#else
+extern "C" int smo_kdyn_peer_handle_bytes(void) { return 64 * (2 * MAXF + 1); }
+extern "C" int smo_kdyn_peer_export(smo_kdyn_t*, void*) { return fail(SMO_E_UNSUPPORTED, "no peer memory in the host emulation"); }
+extern "C" int smo_kdyn_peer_attach(smo_kdyn_t*, const void*) { return fail(SMO_E_UNSUPPORTED, "no peer memory in the host emulation"); }
+#endif
+
 extern "C" int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj) {
   if (!h) return fail(SMO_E_ARG, "smo_kdyn_set_chunks: null handle");
   h->chunks_fwd = chunks_fwd; h->chunks_adj = chunks_adj;

@@ -33,6 +33,7 @@ namespace smo {
 typedef double2 cplx;   // interleaved (re, im)
 
 constexpr int MAXF = 6;  // max fields handled by one launch
+constexpr int MAXP = 8;  // max ranks (GPUs of one box) of the slab decomposition
 
 template <class T> SMO_HD T ldg(const T* p) {
 #if defined(__CUDA_ARCH__)

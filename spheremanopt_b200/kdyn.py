@@ -33,7 +33,7 @@ def _dist():
 class Domain:
     """Stand-in for the dedalus domain of KD:212-216 (three Fourier bases, Npts modes each, dealias 3/2)."""
 
-    def __init__(self, Npts, X=(0., 2. * np.pi), device=None, distributed=None):
+    def __init__(self, Npts, X=(0., 2. * np.pi), device=None, distributed=None, peer_memory=True):
         self.lib = _cabi.load()
         self.N = int(Npts)
         self.dealias = 3 / 2
@@ -66,6 +66,28 @@ class Domain:
             h = C.c_void_p()
             _cabi.check(self.lib, self.lib.smo_kdyn_create(C.byref(h), self.N, self.L, self.rank, self.nranks, self.comm))
         self.h = h
+        self.peer = False
+        if self.nranks > 1 and peer_memory:
+            # fused transposes: exchange CUDA IPC handles of the pencil buffers so that the FFT passes store straight
+            # into the peers' memory over NVLink (falls back to grouped ncclSend/ncclRecv if IPC is unavailable)
+            with torch.cuda.device(self.device):
+                nb = self.lib.smo_kdyn_peer_handle_bytes()
+                mine = (C.c_ubyte * nb)()
+                ok = self.lib.smo_kdyn_peer_export(h, mine) == 0
+                t = torch.tensor(list(mine) + [1 if ok else 0], dtype=torch.uint8, device=self.device)
+                parts = [torch.empty_like(t) for _ in range(self.nranks)]
+                dist.all_gather(parts, t)
+                allb = torch.stack(parts).cpu()
+                if bool(allb[:, -1].all()):
+                    blob = (C.c_ubyte * (nb * self.nranks))(*allb[:, :-1].reshape(-1).tolist())
+                    ok = self.lib.smo_kdyn_peer_attach(h, blob) == 0
+                else:
+                    ok = False
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) != 1:
+                    raise RuntimeError("peer-memory attachment failed on some rank: %s" % self.lib.smo_last_error().decode())
+                self.peer = True
         self.nz = self.M // self.nranks
         self.z0 = self.rank * self.nz
         self.nkx = self.Nh // self.nranks
