@@ -120,6 +120,10 @@ int smo_kdyn_peer_attach(smo_kdyn_t* h, const void* all_handles);
 /* tuning: number of z chunks of the y-pass -> fused x-pass -> y-pass sequence of a forward / adjoint step (keeps the
  * y-padded arrays L2 resident); -1 = choose from the problem size, 1 = off (default) */
 int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
+/* tuning / A-B switches.  SMO_OPT_FUSED_Z: 1 (default) = forward-z FFT + implicit update + inverse-z FFT of a time step
+ * run as ONE kernel (csrc/zstep.cuh); 0 = the three separate kernels. */
+#define SMO_OPT_FUSED_Z 1
+int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);
 

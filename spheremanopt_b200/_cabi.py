@@ -53,6 +53,7 @@ SIGNATURES = {
     "smo_kdyn_peer_attach": (i32, [vp, vp]),
     "smo_kdyn_set_chunks": (i32, [vp, i32, i32]),
     "smo_kdyn_use_graph": (i32, [vp, i32]),
+    "smo_kdyn_set_option": (i32, [vp, i32, i32]),
     # communicator (multi-GPU slab decomposition)
     "smo_comm_unique_id_bytes": (i32, []),
     "smo_comm_get_unique_id": (i32, [vp]),
@@ -68,6 +69,7 @@ SIGNATURES = {
 
 SMO_ADJOINT_CONTINUOUS = 1
 SMO_COST_INTEGRATED = 2
+SMO_OPT_FUSED_Z = 1
 
 
 def bind(cdll):

@@ -9,6 +9,7 @@
 #include "fft_pass.cuh"
 #include "xpass.cuh"
 #include "kd_epilogue.cuh"
+#include "zstep.cuh"
 #include "sh23.cuh"
 #include "reduce.cuh"
 
@@ -443,9 +444,10 @@ struct smo_kdyn {
   cplx* peer_p1[MAXF][MAXP]; cplx* peer_p1t[MAXF][MAXP];
   unsigned long long* flags; unsigned long long* peer_flags[MAXP]; unsigned long long epoch;
   int chunks_fwd, chunks_adj;   // z-chunked y/x/y sequence (L2-resident P2 arrays); <= 1: whole slab at once
+  int fused_z;                  // 1 (default): forward-z + implicit update + inverse-z of a time step in one kernel (zstep.cuh)
 };
 
-enum { PK_Z = 1, PK_Y = 2, PK_X = 3, PK_EPI = 4, PK_A2A = 5, PK_XA = 6 };
+enum { PK_Z = 1, PK_Y = 2, PK_X = 3, PK_EPI = 4, PK_A2A = 5, PK_XA = 6, PK_ZS = 7 };
 
 #if !defined(SMO_EMUL)
 static void prof_begin(smo_kdyn* h, int kind, rt_stream st) {
@@ -552,6 +554,9 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 #ifndef SMO_TXA
 #define SMO_TXA 4
 #endif
+#ifndef SMO_TZS
+#define SMO_TZS 2
+#endif
 // ---- pass launchers ---------------------------------------------------------------------------------------
 template <int M> struct KdOps {
   typedef typename FacOf<M>::type F;
@@ -559,6 +564,7 @@ template <int M> struct KdOps {
   static constexpr int TY = SMO_TY;    // lines per CTA, strided (y) passes
   static constexpr int TX = SMO_TX;    // columns per CTA, x passes with <= 3 fields
   static constexpr int TXA = SMO_TXA;  // columns per CTA, fused adjoint x pass (6 fields)
+  static constexpr int TZS = SMO_TZS;  // lines per CTA (x 3 components), fused z step
 
   static void fill(PassParams& p, smo_kdyn* h, int nf) {
     memset(&p, 0, sizeof p);
@@ -703,6 +709,50 @@ template <int M> struct KdOps {
     TRY(inv_y(h, h->p1t, h->p2, 3, st));
     return x_c2r(h, h->p2, g, st);
   }
+  // fused z step (zstep.cuh): p1 -> [forward z FFT, implicit update of the state, inverse z FFT] -> p1
+  //   mode 0: state Bn -> Bnp1 (3 fields);  mode 1: state G, NU in place (6 fields), nxt = next forward snapshot
+  static int zstep(smo_kdyn* h, int mode, const cplx* const* Bn, cplx* const* Bnp1, const cplx* const* nxt, bool do_inv,
+                   double Rm, double dt, rt_stream st) {
+    ZParams p; memset(&p, 0, sizeof p);
+    const int nf = mode == 0 ? 3 : 6;
+    for (int f = 0; f < nf; ++f) { p.in[f] = h->p1[f]; p.out[f] = h->p1[f]; }
+    if (mode == 0) {
+      for (int c = 0; c < 3; ++c) { p.b[c] = Bn[c]; p.o[c] = Bnp1[c]; }
+    } else {
+      for (int c = 0; c < 3; ++c) {
+        p.b[c] = h->G[c]; p.o[c] = h->G[c]; p.b[3 + c] = h->NU[c]; p.o[3 + c] = h->NU[c];
+        p.nxt[c] = nxt ? nxt[c] : nullptr;
+      }
+    }
+    p.nsteps = 1; p.mode = mode; p.ntrip = mode == 0 ? 1 : 2;
+    p.nlines = h->nkx * h->Nc; p.tiles = (p.nlines + TZS - 1) / TZS; p.nwork = p.tiles * p.ntrip;
+    p.do_inv = do_inv ? 1 : 0;
+    p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
+    p.line_stride = h->nz; p.kfac = h->kfac; p.Rm = Rm; p.dt = dt; p.scale = 1.0 / M; p.tw = h->tw;
+    if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
+    if (h->peer_on) {
+      p.peer_mode = 1; p.peer_off = (long long)h->rank * p.blk;
+      for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_out[f][s2] = h->peer_p1t[f][s2];
+    }
+    prof_begin(h, PK_ZS, st);
+    int rc = launch<ZStep<F, TZS>>(p, st);
+    prof_end(h, PK_ZS, st);
+    return rc;
+  }
+  // y -> fused x -> y part of a step: p1t (z-slab side) -> p1t
+  static int yxy(smo_kdyn* h, int nf, rt_stream st) {
+    const int tile = nf == 3 ? TX : (TXA > TY ? TXA : TY);
+    const int nch = pick_chunks(h, nf == 3 ? h->chunks_fwd : h->chunks_adj, nf, tile);
+    const int nzc = h->nz / nch;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int z0 = ch * nzc;
+      TRY(inv_y(h, h->p1t, h->p2, nf, st, z0, nch > 1 ? nzc : -1));
+      if (nf == 3) TRY(x_fwd(h, h->p2, st, z0, nch > 1 ? nzc : -1));
+      else TRY(x_adj(h, h->p2, st, z0, nch > 1 ? nzc : -1));
+      TRY(fwd_y(h, h->p2, h->p1t, nf, st, z0, nch > 1 ? nzc : -1));
+    }
+    return 0;
+  }
   static void efill(EpiParams& p, smo_kdyn* h, double Rm, double dt, int flag) {
     memset(&p, 0, sizeof p);
     p.nsteps = 1; p.n = (long long)h->csize; p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
@@ -785,17 +835,43 @@ template <int M> static int kd_set_U(smo_kdyn* h, const double* U, rt_stream st)
   h->have_U = true;
   return 0;
 }
+// Time loop of the forward problem with the fused z step: the state travels  coefficients -> p1 -> p2 -> (x pass) -> p2
+// -> p1 -> [zstep: coefficients of step n+1 written to state(n+1), and already on their way back to p1].
+// state(n) returns the three coefficient arrays of step n.
+template <int M, class StateFn>
+static int kd_forward_loop(smo_kdyn* h, int n_steps, double Rm, double dt, StateFn state, rt_stream st) {
+  if (n_steps <= 0) return 0;
+  if (!h->fused_z) {
+    for (int n = 0; n < n_steps; ++n) TRY(KdOps<M>::fwd_step(h, state(n), state(n + 1), Rm, dt, st));
+    return 0;
+  }
+  TRY(KdOps<M>::inv_z(h, state(0), h->p1, 3, st));
+  TRY(a2a(h, h->p1, h->p1t, 3, st));
+  for (int n = 0; n < n_steps; ++n) {
+    TRY(KdOps<M>::yxy(h, 3, st));
+    TRY(a2a(h, h->p1t, h->p1, 3, st));
+    const bool more = n + 1 < n_steps;
+    TRY(KdOps<M>::zstep(h, 0, state(n), state(n + 1), nullptr, more, Rm, dt, st));
+    if (more) TRY(a2a(h, h->p1, h->p1t, 3, st));
+  }
+  return 0;
+}
+struct SnapState {
+  smo_kdyn* h; void* snaps; cplx* cur[2][3]; int flip;
+  cplx* const* operator()(int n) { flip ^= 1; snap_ptrs(h, snaps, n, cur[flip]); return cur[flip]; }
+};
+struct PingPong {
+  cplx** a; cplx** b;
+  cplx* const* operator()(int n) { return (n & 1) ? b : a; }
+};
 template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                                        void* snaps, double* J_host, rt_stream st) {
   TRY(kd_set_U<M>(h, U, st));
-  cplx* s0[3]; cplx* s1[3];
+  cplx* s0[3];
   snap_ptrs(h, snaps, 0, s0);
   TRY(KdOps<M>::to_coef(h, B0, s0, st));
-  for (int n = 0; n < n_iters; ++n) {
-    snap_ptrs(h, snaps, n, s0);
-    snap_ptrs(h, snaps, n + 1, s1);
-    TRY(KdOps<M>::fwd_step(h, s0, s1, Rm, dt, st));
-  }
+  SnapState state; state.h = h; state.snaps = snaps; state.flip = 0;
+  TRY((kd_forward_loop<M>(h, n_iters, Rm, dt, state, st)));
   // Cost "Final": J = mean over the dealiased grid of |B^N|^2 (FWD_Solve_KDyn.py:622, 671-673)
   snap_ptrs(h, snaps, n_iters, s0);
   TRY(KdOps<M>::to_grid(h, s0, h->gwork, st));
@@ -807,13 +883,10 @@ template <int M> static int kd_prep(smo_kdyn* h, const double* B0, const double*
                                     double* out, rt_stream st) {
   TRY(kd_set_U<M>(h, U, st));
   // ping-pong between G and NU as coefficient state (no snapshots kept)
-  cplx** a = h->G; cplx** b = h->NU;
-  TRY(KdOps<M>::to_coef(h, B0, a, st));
-  for (int n = 0; n < n_iters + 1; ++n) {
-    TRY(KdOps<M>::fwd_step(h, a, b, Rm, dt, st));
-    cplx** t = a; a = b; b = t;
-  }
-  return KdOps<M>::to_grid(h, a, out, st);
+  PingPong state; state.a = h->G; state.b = h->NU;
+  TRY(KdOps<M>::to_coef(h, B0, h->G, st));
+  TRY((kd_forward_loop<M>(h, n_iters + 1, Rm, dt, state, st)));
+  return KdOps<M>::to_grid(h, state(n_iters + 1), out, st);
 }
 template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_iters, const void* snaps, double* gB,
                                        double* gU, int flags, rt_stream st) {
@@ -822,10 +895,26 @@ template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_
   snap_ptrs(h, const_cast<void*>(snaps), n_iters, s);
   TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
   for (int c = 0; c < 3; ++c) TRY(rt_memset(h->NU[c], 0, sizeof(cplx) * h->csize, st));
-  for (int m = 0; m < n_iters; ++m) {
-    const int idx = cont ? (n_iters - m) : (n_iters - 1 - m);   // snapshot_index -1-m / -2-m
-    snap_ptrs(h, const_cast<void*>(snaps), idx, s);
-    TRY(KdOps<M>::adj_step(h, s, Rm, dt, 0, st));
+  // adjoint step m linearises about snapshot idx(m): snapshot_index -1-m (continuous) / -2-m (discrete)
+  auto idx = [&](int m) { return cont ? (n_iters - m) : (n_iters - 1 - m); };
+  if (!h->fused_z) {
+    for (int m = 0; m < n_iters; ++m) {
+      snap_ptrs(h, const_cast<void*>(snaps), idx(m), s);
+      TRY(KdOps<M>::adj_step(h, s, Rm, dt, 0, st));
+    }
+  } else if (n_iters > 0) {
+    snap_ptrs(h, const_cast<void*>(snaps), idx(0), s);
+    const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], s[0], s[1], s[2]};
+    TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, st));
+    TRY(a2a(h, h->p1, h->p1t, 6, st));
+    for (int m = 0; m < n_iters; ++m) {
+      TRY(KdOps<M>::yxy(h, 6, st));
+      TRY(a2a(h, h->p1t, h->p1, 6, st));
+      const bool more = m + 1 < n_iters;
+      if (more) snap_ptrs(h, const_cast<void*>(snaps), idx(m + 1), s);
+      TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more ? s : nullptr, more, Rm, dt, st));
+      if (more) TRY(a2a(h, h->p1, h->p1t, 6, st));
+    }
   }
   TRY(KdOps<M>::final_scale(h, Rm, dt, cont, st));
   TRY(KdOps<M>::to_grid(h, h->cw, gB, st));
@@ -870,6 +959,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
   for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
   for (int s2 = 0; s2 < MAXP; ++s2) h->peer_flags[s2] = nullptr;
+  h->fused_z = 1;
   h->chunks_fwd = h->chunks_adj = 1;    // off by default (measured slower at 128^3: the passes are not HBM-bound enough to gain)
   h->hB = h->hU = h->hGB = h->hGU = nullptr; h->snaps = nullptr; h->cap_snap = 0;
   h->tw = nullptr; h->gwork = nullptr; h->vwork = nullptr;
@@ -1078,6 +1168,13 @@ extern "C" int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj
   if (!h) return fail(SMO_E_ARG, "smo_kdyn_set_chunks: null handle");
   h->chunks_fwd = chunks_fwd; h->chunks_adj = chunks_adj;
   return 0;
+}
+extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
+  if (!h) return fail(SMO_E_ARG, "smo_kdyn_set_option: null handle");
+  switch (key) {
+    case SMO_OPT_FUSED_Z: h->fused_z = value ? 1 : 0; return 0;
+    default: return fail(SMO_E_ARG, "smo_kdyn_set_option: unknown key %d", key);
+  }
 }
 extern "C" int smo_kdyn_use_graph(smo_kdyn_t* h, int on) {
   if (!h) return fail(SMO_E_ARG, "smo_kdyn_use_graph: null handle");

@@ -1,0 +1,271 @@
+// Fused z pass of the kinematic-dynamo time loops: forward FFT along z + truncation, the diagonal-in-Fourier
+// implicit update of the time stepper, and the zero-padded inverse FFT along z of the NEXT step's operands - one
+// kernel, one HBM round trip of the pencil data per time step.
+//
+// Replaces, per time step of FWD_Solve_KDyn.py:635-641 (forward) and :955-961 (adjoint), the sequence
+//   FftPass<-1> (p1 -> coefficients)  +  EpiKernel<EPI_FWD / EPI_ADJ>  +  FftPass<+1> (coefficients -> p1)
+// of the unfused path: the right-hand side coefficients never travel to HBM, the state (B^n | G, nu) is read once
+// and written once, and what the next step needs on the grid side (B^{n+1} | curl G', B_f of the next snapshot)
+// goes straight from shared memory into the inverse transform.
+//
+// A work item is a *triplet*: the three vector components of T adjacent z lines (a z line = all kz of one (kx, ky)).
+//   forward step : 1 triplet per tile  - in = to_p1(U x B^n),        state B^n -> B^{n+1},   next operand B^{n+1}
+//   adjoint step : 2 triplets per tile - in = to_p1((curl G) x U),   state G -> G',          next operand curl G'
+//                                        in = to_p1((curl G) x B_f), state nu -> nu',        next operand B_f (next snapshot)
+// Thread (f, t, jj): component f, line t, stage thread jj < RT.  With RT dividing 32 all exchanges of a line stay
+// inside one warp, so only the two barriers around the pointwise update (which mixes the three components) are
+// CTA-wide; everything else is a __syncwarp (smo_common.cuh: sync_after).
+// Shared memory: landing buffer [3][T][M] (cp.async target of the NEXT tile, prefetched as soon as stage 1 has
+// consumed the current one), work buffer [3][T][XP] (exchange -> compact coefficients -> exchange), twiddles, maps.
+#pragma once
+#include "fft_core.cuh"
+#include "kd_epilogue.cuh"
+
+#ifndef SMO_ZS_MB
+#define SMO_ZS_MB 5     // resident CTAs per SM the register allocation of the fused z step is bounded for
+#endif
+
+namespace smo {
+
+struct ZParams {
+  const cplx* in[MAXF];     // p1 inputs (kx-slab side), one per field
+  cplx* out[MAXF];          // p1 outputs (local buffer; peer buffers below when peer_mode != 0)
+  const cplx* b[MAXF];      // coefficient state in  : forward B^n[3]    | adjoint G[3], nu[3]
+  cplx* o[MAXF];            // coefficient state out : forward B^{n+1}[3] | adjoint G'[3], nu'[3]
+  const cplx* nxt[3];       // adjoint: forward-state snapshot the next adjoint step linearises about
+  int nwork, nsteps;        // nwork = tiles * ntrip
+  int ntrip, mode;          // mode 0: forward CNAB1 step (ntrip 1); mode 1: adjoint step (ntrip 2)
+  int nlines, tiles;        // z lines of this rank = nkx*Nc
+  int do_inv;               // 0: last step of a loop, nothing follows on the grid side
+  int Nc, Pc, kmax, kx0;
+  int line_stride;          // p1 elements between consecutive lines inside a block (= nz)
+  int seglen;               // multi-rank p1 layout [s][nkx][Nc][nz]: z index n lives in block n / seglen (0: one rank)
+  long long blk;
+  double kfac, Rm, dt, scale;
+  const cplx* tw;
+  int peer_mode;            // 1: segment s of every output line is stored straight into rank s's buffer
+  long long peer_off;
+  cplx* peer_out[MAXF][MAXP];
+};
+
+template <class F, int T_> struct ZStep {
+  typedef ZParams Params;
+  static constexpr bool V2 = true;
+  static constexpr int T = T_, M = F::M, R1 = F::R1, R2 = F::R2, RT = F::RT, XP = F::XP;
+  static constexpr int KMAX = M / 3 - 1, NC = 2 * KMAX + 1, PC = NC + 1;
+  static constexpr int THREADS = 3 * T_ * F::RT;
+  static constexpr int NPHASES = 9;
+  static constexpr int MIN_BLOCKS = SMO_ZS_MB;
+  static constexpr bool WARP_OK = (32 % F::RT == 0);       // the RT threads of a line never straddle a warp
+  static constexpr int LAND = 3 * T_ * M, WORK = 3 * T_ * XP;
+  static constexpr size_t SMEM = (size_t)(LAND + WORK + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int);
+  static_assert(XP >= PC, "compact coefficient line must fit into the exchange line");
+  struct State {
+    double re[F::RT], im[F::RT];
+    int it;
+  };
+  // barrier after phase PH: 1 = warp, 2 = CTA
+  SMO_HD static constexpr int sync_after(int ph) { return (!WARP_OK || ph == 4 || ph == 5) ? 2 : 1; }
+
+  SMO_HD static cplx* land(unsigned char* s) { return reinterpret_cast<cplx*>(s); }
+  SMO_HD static cplx* wrk(unsigned char* s) { return land(s) + LAND; }
+  SMO_HD static cplx* twid(unsigned char* s) { return wrk(s) + WORK; }
+  SMO_HD static int* segidx(unsigned char* s) { return reinterpret_cast<int*>(twid(s) + M); }   // n / seglen
+  SMO_HD static int* segrem(unsigned char* s) { return segidx(s) + M; }                         // n % seglen
+
+  SMO_HD static void split_tid(int tid, int& f, int& t, int& jj) {
+    jj = tid % RT;
+    t = (tid / RT) % T;
+    f = tid / (RT * T);
+  }
+  SMO_HD static void decode(const Params& p, int work, int& tile, int& trip) {
+    tile = work / p.ntrip;
+    trip = work - tile * p.ntrip;
+  }
+  // the thread's own line of the landing buffer <- p1 line (asynchronous; only the RT threads of a line touch it)
+  SMO_HD static void load_tile(const Params& p, int work, const Ctx& c) {
+    int f, t, jj, tile, trip;
+    split_tid(c.tid, f, t, jj);
+    decode(p, work, tile, trip);
+    const int b = tile * T + t;
+    if (b >= p.nlines) return;
+    cplx* Ld = land(c.smem) + (f * T + t) * M;
+    const cplx* src = p.in[3 * trip + f] + (long long)b * p.line_stride;
+    if (p.seglen <= 0) {
+      for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], src + e);
+    } else {
+      const int* si = segidx(c.smem);
+      const int* sr = segrem(c.smem);
+      for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], src + (long long)si[e] * p.blk + sr[e]);
+    }
+  }
+
+  SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
+    cplx* W = twid(c.smem);
+    for (int m = c.tid; m < M; m += THREADS) W[m] = ldg_c(p.tw + ((m % R2) * (m / R2)) % M);
+    int* si = segidx(c.smem);
+    int* sr = segrem(c.smem);
+    for (int m = c.tid; m < M; m += THREADS) {
+      si[m] = p.seglen > 0 ? m / p.seglen : 0;
+      sr[m] = p.seglen > 0 ? m % p.seglen : m;
+    }
+    st.it = 0;
+  }
+
+  template <int PH>
+  SMO_HD static void phase2(const Params& p, int work, int /*step*/, const Ctx& c, State& st) {
+    int f, t, jj, tile, trip;
+    split_tid(c.tid, f, t, jj);
+    decode(p, work, tile, trip);
+    const int b = tile * T + t;
+    const bool live = b < p.nlines;
+    cplx* Ld = land(c.smem) + (f * T + t) * M;
+    cplx* Wk = wrk(c.smem) + (f * T + t) * XP;
+    if (PH == 0) {
+      if (st.it == 0) load_tile(p, work, c);
+      cp_async_commit();
+      cp_async_wait<0>();
+    } else if (PH == 1) {
+      // forward stage 1: thread j < R2 owns z samples j + R2*i
+      if (jj < R2 && live) {
+#pragma unroll
+        for (int i = 0; i < R1; ++i) {
+          const cplx v = Ld[jj + R2 * i];
+          st.re[i] = v.x; st.im[i] = v.y;
+        }
+        RegFFT<R1, -1>::run(as_arr<R1>(st.re), as_arr<R1>(st.im));
+        const cplx* W = twid(c.smem) + jj;
+#pragma unroll
+        for (int k1 = 1; k1 < R1; ++k1) {
+          const cplx w = W[k1 * R2];
+          const double a = st.re[k1], bb = st.im[k1];
+          st.re[k1] = a * w.x - bb * w.y;
+          st.im[k1] = a * w.y + bb * w.x;
+        }
+      }
+    } else if (PH == 2) {
+      // the landing line is consumed: stream in the same line of this CTA's next work item
+      if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, c);
+      cp_async_commit();
+      if (jj < R2 && live) {
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) Wk[jj * F::SK + k1] = make_double2(st.re[k1], st.im[k1]);
+      }
+    } else if (PH == 3) {
+      if (jj < R1 && live) {
+#pragma unroll
+        for (int j = 0; j < R2; ++j) {
+          const cplx v = Wk[j * F::SK + jj];
+          st.re[j] = v.x; st.im[j] = v.y;
+        }
+        stage2<F, -1>(st.re, st.im);
+      }
+    } else if (PH == 4) {
+      // truncate: retained modes, scaled, in the compact order [0..kmax, -kmax..-1] (overwrites the exchange line)
+      if (jj < R1 && live) {
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+          const int cidx = compact_index(jj + R1 * k2, M, KMAX);
+          if (cidx >= 0) Wk[cidx] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
+        }
+      }
+    } else if (PH == 5) {
+      // pointwise implicit update of the three components at (line, kz); consecutive threads -> consecutive kz
+      const int kind = (p.mode == 0) ? 0 : 1 + trip;
+      cplx* Wt = wrk(c.smem);
+      for (int e = c.tid; e < T * PC; e += THREADS) {
+        const int tt = e / PC, iz = e - tt * PC;
+        const int bl = tile * T + tt;
+        if (bl >= p.nlines || iz >= NC) continue;
+        const int ix = bl / p.Nc, iy = bl - ix * p.Nc;
+        Wave w;
+        w.kx = p.kfac * (double)(p.kx0 + ix);
+        w.ky = p.kfac * (double)(iy <= p.kmax ? iy : iy - p.Nc);
+        w.kz = p.kfac * (double)(iz <= p.kmax ? iz : iz - p.Nc);
+        w.k2 = w.kx * w.kx + w.ky * w.ky + w.kz * w.kz;
+        w.valid = true;
+        const bool k0 = (w.k2 == 0.0);
+        const long long idx = (long long)bl * p.Pc + iz;
+        cplx* w0 = Wt + (0 * T + tt) * XP + iz;
+        cplx* w1 = Wt + (1 * T + tt) * XP + iz;
+        cplx* w2 = Wt + (2 * T + tt) * XP + iz;
+        C3 A; A.x = *w0; A.y = *w1; A.z = *w2;
+        C3 nw = zero3(), so = zero3();    // next operand (-> inverse transform), new state (-> HBM)
+        const int sb = 3 * trip;
+        if (kind == 2 && p.do_inv) nw = load3(p.nxt, 0, idx);
+        if (!k0) {
+          const C3 S = load3(p.b, sb, idx);
+          if (kind == 0) {
+            const double alpha = 1.0 / p.dt + w.k2 / (2.0 * p.Rm), beta = 1.0 / p.dt - w.k2 / (2.0 * p.Rm);
+            so = proj_scale_minus(w, axpy3(beta, S, curl3(w, A)), 1.0 / alpha, kdot_over_k2(w, S));
+            nw = so;
+          } else if (kind == 1) {
+            const double alpha = 1.0 / p.dt + w.k2 / (2.0 * p.Rm), beta = 1.0 / p.dt - w.k2 / (2.0 * p.Rm);
+            so = proj_scale_minus(w, axpy3(beta, S, A), 1.0 / alpha, kdot_over_k2(w, S));
+            nw = curl3(w, so);
+          } else {
+            so = proj_scale_minus(w, axpy3(-p.dt, A, S), 1.0, kdot_over_k2(w, S));
+          }
+        }
+        store3(p.o, sb, idx, so);
+        *w0 = nw.x; *w1 = nw.y; *w2 = nw.z;
+      }
+    } else if (PH == 6) {
+      // inverse stage 1 on the zero-padded compact line
+      if (p.do_inv && jj < R2 && live) {
+#pragma unroll
+        for (int i = 0; i < R1; ++i) {
+          const int n = jj + R2 * i;
+          cplx v = make_double2(0.0, 0.0);
+          if (n <= KMAX) v = Wk[n];
+          else if (n >= M - KMAX) v = Wk[n - (M - NC)];
+          st.re[i] = v.x; st.im[i] = v.y;
+        }
+        RegFFT<R1, +1>::run(as_arr<R1>(st.re), as_arr<R1>(st.im));
+        const cplx* W = twid(c.smem) + jj;
+#pragma unroll
+        for (int k1 = 1; k1 < R1; ++k1) {
+          const cplx w = W[k1 * R2];
+          const double a = st.re[k1], bb = st.im[k1];
+          st.re[k1] = a * w.x + bb * w.y;
+          st.im[k1] = bb * w.x - a * w.y;
+        }
+      }
+    } else if (PH == 7) {
+      if (p.do_inv && jj < R2 && live) {
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) Wk[jj * F::SK + k1] = make_double2(st.re[k1], st.im[k1]);
+      }
+    } else {
+      if (p.do_inv && jj < R1 && live) {
+#pragma unroll
+        for (int j = 0; j < R2; ++j) {
+          const cplx v = Wk[j * F::SK + jj];
+          st.re[j] = v.x; st.im[j] = v.y;
+        }
+        stage2<F, +1>(st.re, st.im);
+        const int fo = 3 * trip + f;
+        const int* si = segidx(c.smem);
+        const int* sr = segrem(c.smem);
+        const long long line = (long long)b * p.line_stride;
+        if (p.peer_mode == 1) {
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) {
+            const int k = jj + R1 * k2;
+            p.peer_out[fo][si[k]][p.peer_off + line + sr[k]] = make_double2(st.re[k2], st.im[k2]);
+          }
+        } else {
+          cplx* dst = p.out[fo] + line;
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) {
+            const int k = jj + R1 * k2;
+            dst[(long long)si[k] * p.blk + sr[k]] = make_double2(st.re[k2], st.im[k2]);
+          }
+        }
+      }
+      st.it++;
+    }
+  }
+};
+
+}  // namespace smo

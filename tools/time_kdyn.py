@@ -28,16 +28,18 @@ B = B / np.sqrt(ip(B)); U = U / np.sqrt(ip(U))
 st = kdyn.GEN_BUFFER(N, dom, nit)
 X = [kdyn.DevVec(B), kdyn.DevVec(U)]
 args = (dom, 10.0, 1e-3, nit, nit, st)
-names = {0: "total", 1: "z-pass", 2: "y-pass", 3: "x-fwd", 4: "epilogue", 5: "a2a", 6: "x-adj"}
+names = {0: "total", 1: "z-pass", 2: "y-pass", 3: "x-fwd", 4: "epilogue", 5: "a2a", 6: "x-adj", 7: "z-step"}
 C_ = (N // 2) * (N - 1) ** 2 * 16; P1 = (N // 2) * (N - 1) * M * 16; P2 = (N // 2) * M * M * 16
 alg_f = 9 * C_ + 12 * P1 + 15 * P2; alg_a = 18 * C_ + 24 * P1 + 27 * P2
 import os
 chunk_sets = [tuple(int(v) for v in cs.split(",")) for cs in os.environ.get("CHUNKS", "1,1").split(";")]
+if os.environ.get("FUSED_Z") is not None:
+    lib.smo_kdyn_set_option(dom.h, 1, int(os.environ["FUSED_Z"]))
 kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)   # warm-up (lazy module loading)
 for cf, ca in chunk_sets:
   lib.smo_kdyn_set_chunks(dom.h, cf, ca)
   print("chunks fwd/adj:", cf, ca)
-  for which in ((0, 1, 2, 3, 6, 4) if len(chunk_sets) == 1 else (0,)):
+  for which in ((0, 1, 2, 3, 6, 4, 7) if len(chunk_sets) == 1 else (0,)):
     for fn, nm, alg in ((kdyn.FWD_Solve_IVP_Lin, "fwd", alg_f), (kdyn.ADJ_Solve_IVP_Lin, "adj", alg_a)):
         lib.smo_kdyn_profile_set(dom.h, which)
         torch.cuda.synchronize(); t = time.time()
