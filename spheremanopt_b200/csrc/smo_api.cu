@@ -549,7 +549,7 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 #define SMO_TY 8
 #endif
 #ifndef SMO_TX
-#define SMO_TX 8
+#define SMO_TX 4
 #endif
 #ifndef SMO_TXA
 #define SMO_TXA 4

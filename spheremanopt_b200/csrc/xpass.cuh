@@ -236,8 +236,15 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
   static constexpr int NH = M / 3;                   // retained kx modes (dealias 3/2: Npts/2 = M/3)
   static constexpr int THREADS = NJ * RT;
   static constexpr int NPHASES = 9;
-  static constexpr int MIN_BLOCKS = SMO_X_MB;
+  static constexpr int MIN_BLOCKS = (THREADS <= 96) ? 2 * SMO_X_MB : SMO_X_MB;
   static constexpr int XLEN = (F::XP > FS::XP) ? ((F::XP > M) ? F::XP : M) : ((FS::XP > M) ? FS::XP : M);
+  // With JFAST and exactly one warp per field (FT = 32: both column pairs of a field, 16 stage threads each) every
+  // FFT exchange, the spectral tile and the spectrum hand-over stay inside one warp: only the two barriers around the
+  // product phase (which reads the other fields' grid values and the shared velocity tile) are CTA-wide, so the
+  // warps of a CTA drift apart and overlap each other's shared-memory and fp64 phases.
+  static constexpr int FT = HP * RT;                 // threads per field
+  static constexpr bool WSYNC = JFAST && (FT == 32);
+  SMO_HD static constexpr int sync_after(int ph) { return (!WSYNC || ph == 3 || ph == 4) ? 2 : 1; }
   // Thread order and shared-memory layouts are chosen so that every quarter-warp access is bank-conflict free:
   //   JFAST = false (T = 8): lanes run over the HP = 4 column pairs, then over the stage threads;  X is [e][NJ]
   //   JFAST = true  (T = 4): lanes run over the RT stage threads, then over the HP = 2 pairs;      X is [q][XLP]
@@ -282,7 +289,7 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
     f = tid / (HP * RT);
   }
   SMO_HD static int xe(int e, int q) { return JFAST ? q * XLP + e : e * NJ + q; }                 // exchange / spectrum
-  SMO_HD static int gi(int f, int n, int pp) { return JFAST ? (f * HP + pp) * M + n : (f * M + n) * HP + pp; }   // grid values
+  SMO_HD static int gi(int f, int n, int pp) { return JFAST ? (f * HP + pp) * XLP + n : (f * M + n) * HP + pp; }   // grid values
   SMO_HD static long long tile_of(const Params& p, int work) {
     return (long long)(work / p.tiles_per_row) * p.row_tiles + p.tile0 + (work % p.tiles_per_row);
   }
@@ -290,10 +297,19 @@ template <class F, int T_, int MODE, int NFI, int NFO, bool JFAST> struct XFused
   SMO_HD static void load_sin(const Params& p, int work, const Ctx& c) {
     cplx* S = sin_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
-    for (int q = c.tid; q < NFI * NH * T; q += THREADS) {     // chunks (f, row, column), column fastest
-      const int tc = q % T, r = q / T;
-      const int row = r % NH, f = r / NH;
-      cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+    if constexpr (WSYNC) {                                    // every warp streams in the field it transforms
+      const int f = c.tid / FT;
+      if (f < NFI)
+        for (int q = c.tid % FT; q < NH * T; q += FT) {
+          const int tc = q % T, row = q / T;
+          cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+        }
+    } else {
+      for (int q = c.tid; q < NFI * NH * T; q += THREADS) {   // chunks (f, row, column), column fastest
+        const int tc = q % T, r = q / T;
+        const int row = r % NH, f = r / NH;
+        cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+      }
     }
   }
   SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
