@@ -671,18 +671,18 @@ template <int M> struct KdOps {
     }
   }
   static int x_fwd(smo_kdyn* h, cplx* const* io, rt_stream st, int z0 = 0, int nzc = -1) {
-    XFParams p; xffill(p, h, TX, z0, nzc);
+    XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
     prof_begin(h, PK_X, st);
-    int rc = launch<XFused<F, TX, X_FWD, 3, 3, (TX == 4)>>(p, st);
+    int rc = launch<XFused<F, X_FWD>>(p, st);
     prof_end(h, PK_X, st);
     return rc;
   }
   static int x_adj(smo_kdyn* h, cplx* const* io, rt_stream st, int z0 = 0, int nzc = -1) {
-    XFParams p; xffill(p, h, TXA, z0, nzc);
+    XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 6; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
     prof_begin(h, PK_XA, st);
-    int rc = launch<XFused<F, TXA, X_ADJ, 6, 6, (TXA == 4)>>(p, st);
+    int rc = launch<XFused<F, X_ADJ>>(p, st);
     prof_end(h, PK_XA, st);
     return rc;
   }
