@@ -123,6 +123,9 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* tuning / A-B switches.  SMO_OPT_FUSED_Z: 1 (default) = forward-z FFT + implicit update + inverse-z FFT of a time step
  * run as ONE kernel (csrc/zstep.cuh); 0 = the three separate kernels. */
 #define SMO_OPT_FUSED_Z 1
+/* SMO_OPT_KERNEL_SYNC: 1 (default) = with peer-memory transposes attached, the cross-GPU hand-shakes are fused into the
+ * kernels (the producer's last CTA signals, the consumer's CTAs wait); 0 = one barrier launch per transpose. */
+#define SMO_OPT_KERNEL_SYNC 2
 int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);

@@ -70,6 +70,7 @@ SIGNATURES = {
 SMO_ADJOINT_CONTINUOUS = 1
 SMO_COST_INTEGRATED = 2
 SMO_OPT_FUSED_Z = 1
+SMO_OPT_KERNEL_SYNC = 2
 
 
 def bind(cdll):

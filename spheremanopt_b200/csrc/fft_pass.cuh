@@ -48,6 +48,7 @@ struct PassParams {
   int peer_mode, peer_rows;
   long long peer_off;       // this rank's block inside every peer buffer (rank * blk)
   cplx* peer_out[MAXF][MAXP];
+  XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
 };
 
 template <class F, int DIR, bool TFAST, int T_> struct FftPass {

@@ -444,6 +444,9 @@ struct smo_kdyn {
   cplx* peer_p1[MAXF][MAXP]; cplx* peer_p1t[MAXF][MAXP];
   unsigned long long* flags; unsigned long long* peer_flags[MAXP]; unsigned long long epoch;
   int chunks_fwd, chunks_adj;   // z-chunked y/x/y sequence (L2-resident P2 arrays); <= 1: whole slab at once
+  // in-kernel hand-shakes of the peer-memory transposes (XSync): flag words [0..MAXP) barrier kernel, [MAXP..2MAXP) "p1
+  // filled" (A, signalled by the forward y pass), [2MAXP..3MAXP) "p1t filled" (B, signalled by the z kernels)
+  int inkernel_sync; unsigned long long epochA, epochB; unsigned int* counters;
   int fused_z;                  // 1 (default): forward-z + implicit update + inverse-z of a time step in one kernel (zstep.cuh)
 };
 
@@ -557,6 +560,24 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 #ifndef SMO_TZS
 #define SMO_TZS 2
 #endif
+// ---- in-kernel hand-shakes ----------------------------------------------------------------------------------
+enum { XS_NONE = 0, XS_A = 1, XS_B = 2 };
+static bool kernel_sync(const smo_kdyn* h) { return h->peer_on && h->inkernel_sync; }
+// the launch about to be issued publishes "buffer `which` of every peer is filled by this rank" when it has finished
+static void xs_signal(smo_kdyn* h, XSync& xs, int which) {
+  if (which == XS_NONE || !kernel_sync(h)) return;
+  xs.sig_n = h->nranks; xs.sig_rank = h->rank;
+  xs.sig_epoch = (which == XS_A) ? ++h->epochA : ++h->epochB;
+  for (int s = 0; s < h->nranks; ++s) xs.sig_flags[s] = h->peer_flags[s] + which * MAXP;
+  xs.counter = h->counters + which;
+}
+// the launch about to be issued first waits for the latest signal `which` of every rank
+static void xs_wait(smo_kdyn* h, XSync& xs, int which) {
+  if (which == XS_NONE || !kernel_sync(h)) return;
+  xs.wait_flags = h->flags + which * MAXP; xs.wait_n = h->nranks;
+  xs.wait_epoch = (which == XS_A) ? h->epochA : h->epochB;
+}
+
 // ---- pass launchers ---------------------------------------------------------------------------------------
 template <int M> struct KdOps {
   typedef typename FacOf<M>::type F;
@@ -572,8 +593,9 @@ template <int M> struct KdOps {
     p.in_sN = p.out_sN = 1; p.seglen = 0; p.blk = 0; p.b0 = 0;
   }
   // coefficient [nkx][Nc][Pc] -> p1 [s][nkx][Nc][nz]   (zero-pad + inverse FFT along z)
-  static int inv_z(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st) {
+  static int inv_z(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int sig = XS_NONE) {
     PassParams p; fill(p, h, nf);
+    xs_signal(h, p.xs, sig);
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
     p.nA = 1; p.nB = h->nkx * h->Nc; p.tilesB = (p.nB + TZ - 1) / TZ;
     p.in_sA = 0; p.in_sB = h->Pc;
@@ -605,8 +627,10 @@ template <int M> struct KdOps {
     return rc;
   }
   // p1t [Nh][Nc][nz] -> p2 [Nh][M][nz]   (zero-pad + inverse FFT along y) for the z range [z0, z0+nzc)
-  static int inv_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1) {
+  static int inv_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1,
+                   int wait = XS_NONE) {
     PassParams p; fill(p, h, nf);
+    xs_wait(h, p.xs, wait);
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
     p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
     p.in_sA = (long long)h->Nc * h->nz; p.in_sB = 1; p.in_sN = h->nz;
@@ -617,8 +641,10 @@ template <int M> struct KdOps {
     prof_end(h, PK_Y, st);
     return rc;
   }
-  static int fwd_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1) {
+  static int fwd_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1,
+                   int sig = XS_NONE) {
     PassParams p; fill(p, h, nf);
+    xs_signal(h, p.xs, sig);
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
     p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
     p.in_sA = (long long)M * h->nz; p.in_sB = 1; p.in_sN = h->nz;
@@ -714,6 +740,8 @@ template <int M> struct KdOps {
   static int zstep(smo_kdyn* h, int mode, const cplx* const* Bn, cplx* const* Bnp1, const cplx* const* nxt, bool do_inv,
                    double Rm, double dt, rt_stream st) {
     ZParams p; memset(&p, 0, sizeof p);
+    xs_wait(h, p.xs, XS_A);
+    if (do_inv) xs_signal(h, p.xs, XS_B);
     const int nf = mode == 0 ? 3 : 6;
     for (int f = 0; f < nf; ++f) { p.in[f] = h->p1[f]; p.out[f] = h->p1[f]; }
     if (mode == 0) {
@@ -740,16 +768,17 @@ template <int M> struct KdOps {
     return rc;
   }
   // y -> fused x -> y part of a step: p1t (z-slab side) -> p1t
+  // (with in-kernel hand-shakes the first y pass waits for "p1t filled", the last one signals "p1 filled")
   static int yxy(smo_kdyn* h, int nf, rt_stream st) {
     const int tile = nf == 3 ? TX : (TXA > TY ? TXA : TY);
     const int nch = pick_chunks(h, nf == 3 ? h->chunks_fwd : h->chunks_adj, nf, tile);
     const int nzc = h->nz / nch;
     for (int ch = 0; ch < nch; ++ch) {
       const int z0 = ch * nzc;
-      TRY(inv_y(h, h->p1t, h->p2, nf, st, z0, nch > 1 ? nzc : -1));
+      TRY(inv_y(h, h->p1t, h->p2, nf, st, z0, nch > 1 ? nzc : -1, ch == 0 ? XS_B : XS_NONE));
       if (nf == 3) TRY(x_fwd(h, h->p2, st, z0, nch > 1 ? nzc : -1));
       else TRY(x_adj(h, h->p2, st, z0, nch > 1 ? nzc : -1));
-      TRY(fwd_y(h, h->p2, h->p1t, nf, st, z0, nch > 1 ? nzc : -1));
+      TRY(fwd_y(h, h->p2, h->p1t, nf, st, z0, nch > 1 ? nzc : -1, ch == nch - 1 ? XS_A : XS_NONE));
     }
     return 0;
   }
@@ -845,14 +874,18 @@ static int kd_forward_loop(smo_kdyn* h, int n_steps, double Rm, double dt, State
     for (int n = 0; n < n_steps; ++n) TRY(KdOps<M>::fwd_step(h, state(n), state(n + 1), Rm, dt, st));
     return 0;
   }
-  TRY(KdOps<M>::inv_z(h, state(0), h->p1, 3, st));
-  TRY(a2a(h, h->p1, h->p1t, 3, st));
+  // multi-GPU: the transposes are remote stores of the kernels themselves; their hand-shakes are either fused into the
+  // kernels (ks: producer signals at its end, consumer waits at its start) or separate barrier launches (a2a)
+  const bool ks = kernel_sync(h);
+  if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));     // every rank has left whatever used the pencil buffers before
+  TRY(KdOps<M>::inv_z(h, state(0), h->p1, 3, st, XS_B));
+  if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, st));
   for (int n = 0; n < n_steps; ++n) {
     TRY(KdOps<M>::yxy(h, 3, st));
-    TRY(a2a(h, h->p1t, h->p1, 3, st));
+    if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, st));
     const bool more = n + 1 < n_steps;
     TRY(KdOps<M>::zstep(h, 0, state(n), state(n + 1), nullptr, more, Rm, dt, st));
-    if (more) TRY(a2a(h, h->p1, h->p1t, 3, st));
+    if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 3, st));
   }
   return 0;
 }
@@ -905,15 +938,17 @@ template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_
   } else if (n_iters > 0) {
     snap_ptrs(h, const_cast<void*>(snaps), idx(0), s);
     const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], s[0], s[1], s[2]};
-    TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, st));
-    TRY(a2a(h, h->p1, h->p1t, 6, st));
+    const bool ks = kernel_sync(h);
+    if (ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
+    TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, st, XS_B));
+    if (!ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
     for (int m = 0; m < n_iters; ++m) {
       TRY(KdOps<M>::yxy(h, 6, st));
-      TRY(a2a(h, h->p1t, h->p1, 6, st));
+      if (!ks) TRY(a2a(h, h->p1t, h->p1, 6, st));
       const bool more = m + 1 < n_iters;
       if (more) snap_ptrs(h, const_cast<void*>(snaps), idx(m + 1), s);
       TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more ? s : nullptr, more, Rm, dt, st));
-      if (more) TRY(a2a(h, h->p1, h->p1t, 6, st));
+      if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
     }
   }
   TRY(KdOps<M>::final_scale(h, Rm, dt, cont, st));
@@ -957,6 +992,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
+  h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr;
   for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
   for (int s2 = 0; s2 < MAXP; ++s2) h->peer_flags[s2] = nullptr;
   h->fused_z = 1;
@@ -1010,7 +1046,7 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
       cudaIpcCloseMemHandle(h->peer_flags[s]);
     }
   }
-  rt_free(h->flags);
+  rt_free(h->flags); rt_free(h->counters);
 #endif
   rt_free(h->hB); rt_free(h->hU); rt_free(h->hGB); rt_free(h->hGU); rt_free(h->snaps);
 #if !defined(SMO_EMUL)
@@ -1122,7 +1158,8 @@ extern "C" int smo_kdyn_peer_export(smo_kdyn_t* h, void* out) {
   if (h->nranks < 2) return fail(SMO_E_ARG, "smo_kdyn_peer_export: single-rank handle");
   if (h->nranks > MAXP) return fail(SMO_E_UNSUPPORTED, "peer transposes support at most %d ranks", MAXP);
   if (!h->flags) {
-    TRY(rt_malloc((void**)&h->flags, sizeof(unsigned long long) * MAXP));
+    TRY(rt_malloc((void**)&h->flags, sizeof(unsigned long long) * 3 * MAXP));
+    TRY(rt_malloc((void**)&h->counters, sizeof(unsigned int) * 4));
     CUDA_TRY(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t* hd = (cudaIpcMemHandle_t*)out;
@@ -1173,6 +1210,7 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
   if (!h) return fail(SMO_E_ARG, "smo_kdyn_set_option: null handle");
   switch (key) {
     case SMO_OPT_FUSED_Z: h->fused_z = value ? 1 : 0; return 0;
+    case SMO_OPT_KERNEL_SYNC: h->inkernel_sync = value ? 1 : 0; return 0;
     default: return fail(SMO_E_ARG, "smo_kdyn_set_option: unknown key %d", key);
   }
 }

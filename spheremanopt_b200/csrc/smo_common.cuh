@@ -71,6 +71,25 @@ template <int N> SMO_HD void cp_async_wait() {
 #endif
 }
 
+// Cross-GPU hand-shake fused into a kernel (peer-memory transposes of the slab-decomposed dynamo).  A kernel whose
+// Params carry an `XSync xs` member
+//   * first waits until every source rank has published `wait_epoch` in this GPU's flag words (its inputs were stored
+//     into this GPU's memory by the peers' preceding kernel), and
+//   * after its last CTA has finished, publishes `sig_epoch` in every peer's flag word of this rank (its own remote
+//     stores are complete and visible: per-CTA system fence, completion counter, fence, flag stores).
+// One process per GPU; the waiting kernel only ever waits for kernels running on OTHER GPUs.
+struct XSync {
+  const unsigned long long* wait_flags;   // local flag words, one per source rank; nullptr: no wait
+  unsigned long long wait_epoch;
+  int wait_n;
+  int sig_n, sig_rank;                    // sig_n = 0: no signal
+  unsigned long long sig_epoch;
+  unsigned long long* sig_flags[MAXP];    // the peers' flag arrays
+  unsigned int* counter;                  // local: CTAs of this launch that have finished
+};
+template <class K, class = void> struct has_xsync { static constexpr bool value = false; };
+template <class K> struct has_xsync<K, decltype((void)((typename K::Params*)nullptr)->xs)> { static constexpr bool value = true; };
+
 // what a CTA knows about itself (kernels with K::V2 == true get this instead of a bare tid / smem pair)
 struct Ctx {
   int cta, ncta, tid;
@@ -126,6 +145,16 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const typename K::Params p) {
   extern __shared__ __align__(128) unsigned char smo_smem[];
   typename K::State st;
+  if constexpr (has_xsync<K>::value) {
+    if (p.xs.wait_flags != nullptr) {
+      if ((int)threadIdx.x < p.xs.wait_n) {
+        const volatile unsigned long long* f = p.xs.wait_flags + threadIdx.x;
+        while (*f < p.xs.wait_epoch) { /* spin: the peer's kernel runs on another GPU */ }
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
+  }
   if constexpr (is_v2<K>::value) {
     Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
     K::init(p, c, st);
@@ -134,6 +163,21 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
   for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
     for (int step = 0; step < p.nsteps; ++step)
       PhaseStep<K, 0, false>::run(p, work, step, (int)threadIdx.x, smo_smem, st);
+  }
+  if constexpr (has_xsync<K>::value) {
+    if (p.xs.sig_n > 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int old = atomicAdd(p.xs.counter, 1u);
+        if (old == gridDim.x - 1) {
+          *p.xs.counter = 0u;   // ready for the next launch
+          __threadfence_system();
+          for (int s = 0; s < p.xs.sig_n; ++s)
+            *((volatile unsigned long long*)(p.xs.sig_flags[s] + p.xs.sig_rank)) = p.xs.sig_epoch;
+        }
+      }
+    }
   }
 }
 #else

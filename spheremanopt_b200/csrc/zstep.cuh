@@ -46,6 +46,7 @@ struct ZParams {
   int peer_mode;            // 1: segment s of every output line is stored straight into rank s's buffer
   long long peer_off;
   cplx* peer_out[MAXF][MAXP];
+  XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
 };
 
 template <class F, int T_> struct ZStep {
