@@ -126,6 +126,9 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* SMO_OPT_KERNEL_SYNC: 1 (default) = with peer-memory transposes attached, the cross-GPU hand-shakes are fused into the
  * kernels (the producer's last CTA signals, the consumer's CTAs wait); 0 = one barrier launch per transpose. */
 #define SMO_OPT_KERNEL_SYNC 2
+/* SMO_OPT_PEER_PULL: 0 (default) = peer-memory transposes are fused into the producers' stores (push over NVLink);
+ * 1 = fused into the consumers' loads (cp.async straight out of the peers' buffers, stores stay local). */
+#define SMO_OPT_PEER_PULL 3
 int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);

@@ -71,6 +71,7 @@ SMO_ADJOINT_CONTINUOUS = 1
 SMO_COST_INTEGRATED = 2
 SMO_OPT_FUSED_Z = 1
 SMO_OPT_KERNEL_SYNC = 2
+SMO_OPT_PEER_PULL = 3
 
 
 def bind(cdll):

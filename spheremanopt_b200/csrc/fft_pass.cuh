@@ -45,9 +45,19 @@ struct PassParams {
   // buffers over NVLink instead of a local buffer followed by an all-to-all.
   //   peer_mode 1 (inverse z pass): full-length index k goes to peer k / seglen, at peer_off + line*seglen + k % seglen
   //   peer_mode 2 (forward y pass): row a (= kx) goes to peer a / peer_rows, at peer_off + (a % peer_rows)*out_sA + ...
+  int perm_rows;            // > 0: row order of the work items is interleaved over the perm_rows-row blocks of the peers, so
+                            // that local and remote rows alternate in time instead of coming in bursts
   int peer_mode, peer_rows;
   long long peer_off;       // this rank's block inside every peer buffer (rank * blk)
   cplx* peer_out[MAXF][MAXP];
+  // Transposes fused into the LOADS (pull): the input tile is streamed with cp.async straight out of the peers' buffers
+  // over NVLink; all stores stay local.  Data arrives CTA by CTA, so the transfer of later tiles overlaps the transforms
+  // of earlier ones even when the launch is a single wave.
+  //   pull_mode 1 (forward z pass): full-length index n is read from peer n / seglen, at pull_off + line*seglen + n % seglen
+  //   pull_mode 2 (inverse y pass): row a (= kx) is read from peer a / peer_rows, at pull_off + (a % peer_rows)*in_sA + ...
+  int pull_mode;
+  long long pull_off;
+  const cplx* peer_in[MAXF][MAXP];
   XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
 };
 
@@ -86,6 +96,7 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
     const int r = work - f * per_field;
     a = r / p.tilesB;
     bt = r - a * p.tilesB;
+    if (p.perm_rows > 0) { const int np = p.nA / p.perm_rows; a = (a % np) * p.perm_rows + a / np; }
   }
   SMO_HD static int xidx(int t, int e) { return TFAST ? e * T + t : t * F::XP + e; }
   // offset of full-length index n on a (possibly segmented) side
@@ -103,11 +114,17 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
     const int b = bt * T + t;   // line within this launch
     if (b < p.nB) {
       const cplx* src = p.in[f] + (long long)a * p.in_sA + (long long)(p.b0 + b) * p.in_sB;
+      if (TFAST && PAD && p.pull_mode == 2)
+        src = p.peer_in[f][a / p.peer_rows] + p.pull_off + (long long)(a % p.peer_rows) * p.in_sA + (long long)(p.b0 + b) * p.in_sB;
       if (TFAST) {
         // rows of T adjacent lines: lane t walks along z (16 B each, T*16 B contiguous per row)
         for (int row = jj; row < NIN; row += RT) cp_async16(&B[row * T + t], src + (long long)row * p.in_sN);
       } else if (PAD || p.seglen <= 0) {
         for (int e = jj; e < LENP; e += RT) cp_async16(&B[t * LENP + e], src + e);
+      } else if (p.pull_mode == 1) {
+        const int* so = segtab(c.smem);     // packed (peer << 24 | offset inside the segment)
+        const long long line = p.pull_off + (long long)(p.b0 + b) * p.in_sB;
+        for (int e = jj; e < LENP; e += RT) cp_async16(&B[t * LENP + e], p.peer_in[f][so[e] >> 24] + line + (so[e] & 0xffffff));
       } else {
         const int* so = segtab(c.smem);
         for (int e = jj; e < LENP; e += RT) cp_async16(&B[t * LENP + e], src + so[e]);
@@ -123,7 +140,8 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
     for (int m = c.tid; m < M; m += THREADS) W[m] = ldg_c(p.tw + ((m % R2) * (m / R2)) % M);
     if (!TFAST) {
       int* so = segtab(c.smem);
-      for (int m = c.tid; m < M; m += THREADS) so[m] = (int)full_off(p, m, 1);
+      for (int m = c.tid; m < M; m += THREADS)
+        so[m] = (!PAD && p.pull_mode == 1) ? (((m / p.seglen) << 24) | (m % p.seglen)) : (int)full_off(p, m, 1);
     }
     // per-thread output map of stage 2 (thread k1 = jj holds X[k1 + R1*k2])
 #pragma unroll

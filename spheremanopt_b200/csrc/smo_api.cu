@@ -447,6 +447,7 @@ struct smo_kdyn {
   // in-kernel hand-shakes of the peer-memory transposes (XSync): flag words [0..MAXP) barrier kernel, [MAXP..2MAXP) "p1
   // filled" (A, signalled by the forward y pass), [2MAXP..3MAXP) "p1t filled" (B, signalled by the z kernels)
   int inkernel_sync; unsigned long long epochA, epochB; unsigned int* counters;
+  int peer_pull;                // 0 (default, measured faster on 2 B200): producers push; 1: consumers pull from the peers' buffers
   int fused_z;                  // 1 (default): forward-z + implicit update + inverse-z of a time step in one kernel (zstep.cuh)
 };
 
@@ -566,7 +567,7 @@ static bool kernel_sync(const smo_kdyn* h) { return h->peer_on && h->inkernel_sy
 // the launch about to be issued publishes "buffer `which` of every peer is filled by this rank" when it has finished
 static void xs_signal(smo_kdyn* h, XSync& xs, int which) {
   if (which == XS_NONE || !kernel_sync(h)) return;
-  xs.sig_n = h->nranks; xs.sig_rank = h->rank;
+  xs.sig_n = h->nranks; xs.sig_rank = h->rank; xs.sig_sys = h->peer_pull ? 0 : 1;
   xs.sig_epoch = (which == XS_A) ? ++h->epochA : ++h->epochB;
   for (int s = 0; s < h->nranks; ++s) xs.sig_flags[s] = h->peer_flags[s] + which * MAXP;
   xs.counter = h->counters + which;
@@ -601,7 +602,7 @@ template <int M> struct KdOps {
     p.in_sA = 0; p.in_sB = h->Pc;
     p.out_sA = 0; p.out_sB = h->nz;
     if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
-    if (h->peer_on && out == h->p1) {   // fused transpose: segment s is stored straight into rank s's p1t
+    if (h->peer_on && !h->peer_pull && out == h->p1) {   // fused transpose (push): segment s is stored straight into rank s's p1t
       p.peer_mode = 1; p.peer_off = (long long)h->rank * p.blk;
       for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_out[f][s2] = h->peer_p1t[f][s2];
     }
@@ -620,6 +621,10 @@ template <int M> struct KdOps {
     if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
     p.out_sA = 0; p.out_sB = h->Pc;
     p.scale = 1.0 / M;
+    if (h->peer_on && h->peer_pull && in == h->p1) {   // fused transpose (pull): z segment s is read out of rank s's p1t
+      p.pull_mode = 1; p.pull_off = (long long)h->kx0 * h->Nc * h->nz;
+      for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_in[f][s2] = h->peer_p1t[f][s2];
+    }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Z, st);
     int rc = launch<FftPass<F, -1, false, TZ>>(p, st);
@@ -635,6 +640,10 @@ template <int M> struct KdOps {
     p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
     p.in_sA = (long long)h->Nc * h->nz; p.in_sB = 1; p.in_sN = h->nz;
     p.out_sA = (long long)M * h->nz; p.out_sB = 1; p.out_sN = h->nz;
+    if (h->peer_on && h->peer_pull && in == h->p1t) {   // fused transpose (pull): row kx is read out of its owner's p1
+      p.pull_mode = 2; p.peer_rows = h->nkx; p.perm_rows = h->nkx; p.pull_off = (long long)h->rank * h->nkx * h->Nc * h->nz;
+      for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_in[f][s2] = h->peer_p1[f][s2];
+    }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Y, st);
     int rc = launch<FftPass<F, +1, true, TY>>(p, st);
@@ -650,8 +659,8 @@ template <int M> struct KdOps {
     p.in_sA = (long long)M * h->nz; p.in_sB = 1; p.in_sN = h->nz;
     p.out_sA = (long long)h->Nc * h->nz; p.out_sB = 1; p.out_sN = h->nz;
     p.scale = 1.0 / M;
-    if (h->peer_on && out == h->p1t) {   // fused transpose: row kx is stored straight into its owner's p1
-      p.peer_mode = 2; p.peer_rows = h->nkx; p.peer_off = (long long)h->rank * h->nkx * h->Nc * h->nz;
+    if (h->peer_on && !h->peer_pull && out == h->p1t) {   // fused transpose (push): row kx is stored straight into its owner's p1
+      p.peer_mode = 2; p.peer_rows = h->nkx; p.perm_rows = h->nkx; p.peer_off = (long long)h->rank * h->nkx * h->Nc * h->nz;
       for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_out[f][s2] = h->peer_p1[f][s2];
     }
     p.nwork = nf * p.nA * p.tilesB;
@@ -724,12 +733,14 @@ template <int M> struct KdOps {
   static int to_coef(smo_kdyn* h, const double* grid, cplx* const* coef, rt_stream st) {
     const double* g[3] = {grid, grid + h->gsize, grid + 2 * h->gsize};
     TRY(x_r2c(h, g, h->p2, st));
+    if (h->peer_on) TRY(a2a(h, h->p1t, h->p1, 3, st));   // no peer still uses the buffers the y pass is about to fill
     TRY(fwd_y(h, h->p2, h->p1t, 3, st));
     TRY(a2a(h, h->p1t, h->p1, 3, st));
     return fwd_z(h, h->p1, coef, 3, st);
   }
   static int to_grid(smo_kdyn* h, const cplx* const* coef, double* grid, rt_stream st) {
     double* g[3] = {grid, grid + h->gsize, grid + 2 * h->gsize};
+    if (h->peer_on) TRY(a2a(h, h->p1, h->p1t, 3, st));   // no peer still uses the buffers the z pass is about to fill
     TRY(inv_z(h, coef, h->p1, 3, st));
     TRY(a2a(h, h->p1, h->p1t, 3, st));
     TRY(inv_y(h, h->p1t, h->p2, 3, st));
@@ -758,9 +769,12 @@ template <int M> struct KdOps {
     p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
     p.line_stride = h->nz; p.kfac = h->kfac; p.Rm = Rm; p.dt = dt; p.scale = 1.0 / M; p.tw = h->tw;
     if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
-    if (h->peer_on) {
+    if (h->peer_on && !h->peer_pull) {
       p.peer_mode = 1; p.peer_off = (long long)h->rank * p.blk;
       for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_out[f][s2] = h->peer_p1t[f][s2];
+    } else if (h->peer_on) {
+      p.pull_mode = 1; p.pull_off = (long long)h->kx0 * h->Nc * h->nz;
+      for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_in[f][s2] = h->peer_p1t[f][s2];
     }
     prof_begin(h, PK_ZS, st);
     int rc = launch<ZStep<F, TZS>>(p, st);
@@ -992,7 +1006,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
-  h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr;
+  h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0;
   for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
   for (int s2 = 0; s2 < MAXP; ++s2) h->peer_flags[s2] = nullptr;
   h->fused_z = 1;
@@ -1211,6 +1225,10 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
   switch (key) {
     case SMO_OPT_FUSED_Z: h->fused_z = value ? 1 : 0; return 0;
     case SMO_OPT_KERNEL_SYNC: h->inkernel_sync = value ? 1 : 0; return 0;
+    case SMO_OPT_PEER_PULL: h->peer_pull = value ? 1 : 0; return 0;
+    case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic
+      for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) { h->peer_p1[f][s2] = h->p1[f]; h->peer_p1t[f][s2] = h->p1t[f]; }
+      return 0;
     default: return fail(SMO_E_ARG, "smo_kdyn_set_option: unknown key %d", key);
   }
 }

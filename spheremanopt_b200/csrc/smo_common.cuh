@@ -75,14 +75,19 @@ template <int N> SMO_HD void cp_async_wait() {
 // Params carry an `XSync xs` member
 //   * first waits until every source rank has published `wait_epoch` in this GPU's flag words (its inputs were stored
 //     into this GPU's memory by the peers' preceding kernel), and
-//   * after its last CTA has finished, publishes `sig_epoch` in every peer's flag word of this rank (its own remote
-//     stores are complete and visible: per-CTA system fence, completion counter, fence, flag stores).
+//   * after its last CTA has finished, publishes `sig_epoch` in every peer's flag word of this rank (its stores are
+//     complete and visible: per-CTA fence, completion counter, fence, flag stores).  sig_sys = 1: the data was stored
+//     into the peers' memory (push), the per-CTA fence must be system wide; 0: the data is local and the peers will read
+//     it through this GPU's L2 (pull), a device-wide fence is enough.
+// Measured on 2 B200 (tools/microbench/flag_latency.cu): flag word one way 1.0 us, every system fence +1 us (idle) to
+// +3.4 us (stores in flight); so the waiting side uses no fence at all - its loads are issued after the spin and a CTA
+// barrier, bypass L1 (cp.async.cg / peer addresses) and find the data already in the owning GPU's L2.
 // One process per GPU; the waiting kernel only ever waits for kernels running on OTHER GPUs.
 struct XSync {
   const unsigned long long* wait_flags;   // local flag words, one per source rank; nullptr: no wait
   unsigned long long wait_epoch;
   int wait_n;
-  int sig_n, sig_rank;                    // sig_n = 0: no signal
+  int sig_n, sig_rank, sig_sys;           // sig_n = 0: no signal
   unsigned long long sig_epoch;
   unsigned long long* sig_flags[MAXP];    // the peers' flag arrays
   unsigned int* counter;                  // local: CTAs of this launch that have finished
@@ -150,7 +155,6 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
       if ((int)threadIdx.x < p.xs.wait_n) {
         const volatile unsigned long long* f = p.xs.wait_flags + threadIdx.x;
         while (*f < p.xs.wait_epoch) { /* spin: the peer's kernel runs on another GPU */ }
-        __threadfence_system();
       }
       __syncthreads();
     }
@@ -168,11 +172,11 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
     if (p.xs.sig_n > 0) {
       __syncthreads();
       if (threadIdx.x == 0) {
-        __threadfence_system();
+        if (p.xs.sig_sys) __threadfence_system(); else __threadfence();
         const unsigned int old = atomicAdd(p.xs.counter, 1u);
         if (old == gridDim.x - 1) {
           *p.xs.counter = 0u;   // ready for the next launch
-          __threadfence_system();
+          __threadfence();
           for (int s = 0; s < p.xs.sig_n; ++s)
             *((volatile unsigned long long*)(p.xs.sig_flags[s] + p.xs.sig_rank)) = p.xs.sig_epoch;
         }

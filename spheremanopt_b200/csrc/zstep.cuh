@@ -46,6 +46,9 @@ struct ZParams {
   int peer_mode;            // 1: segment s of every output line is stored straight into rank s's buffer
   long long peer_off;
   cplx* peer_out[MAXF][MAXP];
+  int pull_mode;            // 1: segment s of every input line is read straight out of rank s's buffer (stores stay local)
+  long long pull_off;
+  const cplx* peer_in[MAXF][MAXP];
   XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
 };
 
@@ -94,6 +97,11 @@ template <class F, int T_> struct ZStep {
     const cplx* src = p.in[3 * trip + f] + (long long)b * p.line_stride;
     if (p.seglen <= 0) {
       for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], src + e);
+    } else if (p.pull_mode == 1) {
+      const int* si = segidx(c.smem);
+      const int* sr = segrem(c.smem);
+      const long long line = p.pull_off + (long long)b * p.line_stride;
+      for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], p.peer_in[3 * trip + f][si[e]] + line + sr[e]);
     } else {
       const int* si = segidx(c.smem);
       const int* sr = segrem(c.smem);

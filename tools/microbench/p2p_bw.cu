@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <thread>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
 __global__ void push16(double2* __restrict__ dst, const double2* __restrict__ src, size_t n) {
@@ -142,6 +143,35 @@ int main() {
       const char* nm[] = {"push16", "pushrun", "pull16", "pullcpa", "pushtma", "pulltma", "local16", "localtma"};
       printf("grid %4d %-8s %8.1f GB/s (%.1f us for 64 MiB)\n", g, nm[k], bytes / (best * 1e-3) / 1e9, best * 1e3);
     }
+  }
+  // ---- bidirectional: both GPUs move data at the same time (the all-to-all situation) ----
+  double2 *loc1, *rem0, *loc1b;   // buffers of the mirrored direction
+  CK(cudaSetDevice(1)); CK(cudaDeviceEnablePeerAccess(0, 0)); CK(cudaMalloc(&loc1, bytes)); CK(cudaMalloc(&loc1b, bytes)); CK(cudaMemset(loc1, 3, bytes));
+  CK(cudaSetDevice(0)); CK(cudaMalloc(&rem0, bytes)); CK(cudaMemset(rem0, 4, bytes));
+  for (int k = 0; k < 4; ++k) {
+    float best[2] = {1e9f, 1e9f};
+    for (int rep = 0; rep < 4; ++rep) {
+      float ms[2];
+      auto run = [&](int dev) {
+        cudaSetDevice(dev);
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        double2* L = dev == 0 ? loc : loc1; double2* L2 = dev == 0 ? loc2 : loc1b; double2* R = dev == 0 ? rem : rem0;
+        cudaDeviceSynchronize();
+        cudaEventRecord(a);
+        switch (k) {
+          case 0: push16<<<592, 256>>>(R, L, n); break;
+          case 1: pushrun<<<592, 256>>>(R, L, n); break;
+          case 2: pull16<<<592, 256>>>(L2, R, n); break;
+          case 3: pullcpa<<<592, 256, 4 * 256 * 16>>>(L2, R, n); break;
+        }
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms[dev], a, b);
+      };
+      std::thread t(run, 1); run(0); t.join();
+      for (int d = 0; d < 2; ++d) if (ms[d] < best[d]) best[d] = ms[d];
+    }
+    const char* nm[] = {"push16", "pushrun", "pull16", "pullcpa"};
+    printf("bidirectional %-8s GPU0 %7.1f GB/s  GPU1 %7.1f GB/s\n", nm[k], bytes / (best[0] * 1e-3) / 1e9, bytes / (best[1] * 1e-3) / 1e9);
   }
   return 0;
 }
