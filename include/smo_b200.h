@@ -90,6 +90,15 @@ int smo_kdyn_forward(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, d
  * gradB_dev, gradU_dev: [3][grid_elems] out. */
 int smo_kdyn_adjoint(smo_kdyn_t* h, double Rm, double dt, int n_iters, const void* snaps_dev, double* gradB_dev,
                      double* gradU_dev, int flags, void* stream);
+/* Checkpointed forms of the two calls above (two-level, revolve style; for grids whose n_iters+1 states exceed HBM, e.g.
+ * 256^3 x 1000 steps = 401 GB).  The forward solve keeps the states 0, every, 2*every, ... and N in ckpt_dev
+ * (smo_kdyn_checkpoint_bytes); the adjoint sweep recomputes one segment at a time into seg_dev
+ * (smo_kdyn_snapshot_bytes(h, every) bytes): at most n_iters - every extra forward steps.  Same results bit for bit. */
+size_t smo_kdyn_checkpoint_bytes(const smo_kdyn_t* h, int n_iters, int every);
+int smo_kdyn_forward_ckpt(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, double Rm, double dt, int n_iters,
+                          int every, void* ckpt_dev, double* J_host, int flags, void* stream);
+int smo_kdyn_adjoint_ckpt(smo_kdyn_t* h, double Rm, double dt, int n_iters, int every, const void* ckpt_dev, void* seg_dev,
+                          double* gradB_dev, double* gradU_dev, int flags, void* stream);
 /* Replaces FWD_Solve_IVP_Prep (KD:452-527): n_iters+1 CNAB1 steps from B0 with velocity U; the final field on
  * the grid -> out_dev [3][grid_elems]. */
 int smo_kdyn_prep(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, double Rm, double dt, int n_iters,

@@ -41,6 +41,9 @@ SIGNATURES = {
     "smo_kdyn_forward": (i32, [vp, dp, dp, f64, f64, i32, vp, C.POINTER(f64), i32, vp]),
     "smo_kdyn_adjoint": (i32, [vp, f64, f64, i32, vp, dp, dp, i32, vp]),
     "smo_kdyn_prep": (i32, [vp, dp, dp, f64, f64, i32, dp, vp]),
+    "smo_kdyn_checkpoint_bytes": (sz, [vp, i32, i32]),
+    "smo_kdyn_forward_ckpt": (i32, [vp, dp, dp, f64, f64, i32, i32, vp, C.POINTER(f64), i32, vp]),
+    "smo_kdyn_adjoint_ckpt": (i32, [vp, f64, f64, i32, i32, vp, vp, dp, dp, i32, vp]),
     "smo_kdyn_forward_host": (i32, [vp, dp, dp, f64, f64, i32, vp, C.POINTER(f64), i32, vp]),
     "smo_kdyn_adjoint_host": (i32, [vp, f64, f64, i32, vp, dp, dp, i32, vp]),
     "smo_kdyn_prep_host": (i32, [vp, dp, dp, f64, f64, i32, dp, vp]),

@@ -69,7 +69,7 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
   static constexpr int KMAX = M / 3 - 1, NC = 2 * KMAX + 1;      // dealias 3/2: Npts = 2M/3, kmax = Npts/2 - 1
   static constexpr int THREADS = T_ * F::RT;
   static constexpr int NPHASES = 4;
-  static constexpr int MIN_BLOCKS = (T_ * F::RT <= 64) ? 2 * SMO_PASS_MB : SMO_PASS_MB;
+  static constexpr int MIN_BLOCKS = (F::RT > 16) ? 2 : ((T_ * F::RT <= 64) ? 2 * SMO_PASS_MB : SMO_PASS_MB);   // RT > 16: 48+ doubles per thread
   // input tile: y pass [rows][T]; z pass [T][LENP]
   static constexpr int NIN = PAD ? NC : M;
   static constexpr int LENP = PAD ? NC + 1 : M;

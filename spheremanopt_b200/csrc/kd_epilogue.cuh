@@ -84,13 +84,14 @@ SMO_HD C3 axpy3(double s, const C3& x, const C3& y) {   // s*x + y
   return o;
 }
 
-enum { EPI_FWD = 0, EPI_ADJ = 1, EPI_COMPAT = 2, EPI_FINAL = 3 };
+enum { EPI_FWD = 0, EPI_ADJ = 1, EPI_COMPAT = 2, EPI_FINAL = 3, EPI_CURL = 4 };
 
 // EPI_FWD   : a[0..2] = to_coef(U x B) (EMF), b[0..2] = B^n            -> o[0..2] = B^{n+1}
 // EPI_ADJ   : a[0..2] = to_coef(W x U), a[3..5] = to_coef(W x B_f), b[0..2] = G, b[3..5] = nu
 //             -> o[0..2] = G', o[3..5] = nu', o2[0..2] = i k x G'   (flag&1: "Integrated" cost, o2[3..5] = B_f coeffs)
 // EPI_COMPAT: b[0..2] = B^N -> o[0..2] = G^0, o2[0..2] = i k x G^0   (flag&1 Integrated, flag&2 Continuous)
 // EPI_FINAL : b[0..2] = G^N -> o[0..2] = dt*alpha*G^N  (flag&2 Continuous: plain copy)
+// EPI_CURL  : b[0..2] = G   -> o2[0..2] = i k x G        (segment boundaries of a checkpointed adjoint sweep)
 template <int KIND> struct EpiKernel {
   typedef EpiParams Params;
   static constexpr int THREADS = 256;
@@ -145,6 +146,8 @@ template <int KIND> struct EpiKernel {
       }
       store3(p.o, 0, idx, G);
       store3(p.o2, 0, idx, Wn);
+    } else if (KIND == EPI_CURL) {
+      store3(p.o2, 0, idx, k0 ? zero3() : curl3(w, load3(p.b, 0, idx)));
     } else {
       const C3 G = load3(p.b, 0, idx);
       const double s = (p.flag & 2) ? 1.0 : p.dt * alpha;

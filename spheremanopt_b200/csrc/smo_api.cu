@@ -855,6 +855,11 @@ template <int M> struct KdOps {
     for (int c = 0; c < 3; ++c) { e.b[c] = BN[c]; e.o[c] = h->G[c]; e.o2[c] = h->W[c]; }
     return launch<EpiKernel<EPI_COMPAT>>(e, st);
   }
+  static int curl_G(smo_kdyn* h, double Rm, double dt, rt_stream st) {
+    EpiParams e; efill(e, h, Rm, dt, 0);
+    for (int c = 0; c < 3; ++c) { e.b[c] = h->G[c]; e.o2[c] = h->W[c]; }
+    return launch<EpiKernel<EPI_CURL>>(e, st);
+  }
   static int final_scale(smo_kdyn* h, double Rm, double dt, int flag, rt_stream st) {
     EpiParams e; efill(e, h, Rm, dt, flag);
     for (int c = 0; c < 3; ++c) { e.b[c] = h->G[c]; e.o[c] = h->cw[c]; }
@@ -935,6 +940,38 @@ template <int M> static int kd_prep(smo_kdyn* h, const double* B0, const double*
   TRY((kd_forward_loop<M>(h, n_iters + 1, Rm, dt, state, st)));
   return KdOps<M>::to_grid(h, state(n_iters + 1), out, st);
 }
+// Adjoint time loop over `count` forward states, state(i) = coefficients of the i-th state the sweep linearises about
+// (descending in time).  G, nu (and W = curl G on entry) live in the handle and persist between calls, so a checkpointed
+// sweep can call this once per recomputed segment.
+template <int M, class StateFn>
+static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn state, rt_stream st) {
+  if (count <= 0) return 0;
+  if (!h->fused_z) {
+    for (int i = 0; i < count; ++i) TRY(KdOps<M>::adj_step(h, state(i), Rm, dt, 0, st));
+    return 0;
+  }
+  cplx* const* s = state(0);
+  const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], s[0], s[1], s[2]};
+  const bool ks = kernel_sync(h);
+  if (ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
+  TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, st, XS_B));
+  if (!ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
+  for (int i = 0; i < count; ++i) {
+    TRY(KdOps<M>::yxy(h, 6, st));
+    if (!ks) TRY(a2a(h, h->p1t, h->p1, 6, st));
+    const bool more = i + 1 < count;
+    TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more ? state(i + 1) : nullptr, more, Rm, dt, st));
+    if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
+  }
+  return 0;
+}
+template <int M> static int kd_adjoint_finish(smo_kdyn* h, double Rm, double dt, int cont, double* gB, double* gU, rt_stream st) {
+  TRY(KdOps<M>::final_scale(h, Rm, dt, cont, st));
+  TRY(KdOps<M>::to_grid(h, h->cw, gB, st));
+  TRY(KdOps<M>::to_grid(h, h->NU, gU, st));
+  prof_collect(h, st);
+  return 0;
+}
 template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_iters, const void* snaps, double* gB,
                                        double* gU, int flags, rt_stream st) {
   const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
@@ -943,50 +980,85 @@ template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_
   TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
   for (int c = 0; c < 3; ++c) TRY(rt_memset(h->NU[c], 0, sizeof(cplx) * h->csize, st));
   // adjoint step m linearises about snapshot idx(m): snapshot_index -1-m (continuous) / -2-m (discrete)
-  auto idx = [&](int m) { return cont ? (n_iters - m) : (n_iters - 1 - m); };
-  if (!h->fused_z) {
-    for (int m = 0; m < n_iters; ++m) {
-      snap_ptrs(h, const_cast<void*>(snaps), idx(m), s);
-      TRY(KdOps<M>::adj_step(h, s, Rm, dt, 0, st));
-    }
-  } else if (n_iters > 0) {
-    snap_ptrs(h, const_cast<void*>(snaps), idx(0), s);
-    const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], s[0], s[1], s[2]};
-    const bool ks = kernel_sync(h);
-    if (ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
-    TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, st, XS_B));
-    if (!ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
-    for (int m = 0; m < n_iters; ++m) {
-      TRY(KdOps<M>::yxy(h, 6, st));
-      if (!ks) TRY(a2a(h, h->p1t, h->p1, 6, st));
-      const bool more = m + 1 < n_iters;
-      if (more) snap_ptrs(h, const_cast<void*>(snaps), idx(m + 1), s);
-      TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more ? s : nullptr, more, Rm, dt, st));
-      if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
-    }
-  }
-  TRY(KdOps<M>::final_scale(h, Rm, dt, cont, st));
-  TRY(KdOps<M>::to_grid(h, h->cw, gB, st));
-  TRY(KdOps<M>::to_grid(h, h->NU, gU, st));
-  prof_collect(h, st);
-  return 0;
+  SnapState sn; sn.h = h; sn.snaps = const_cast<void*>(snaps); sn.flip = 0;
+  auto state = [&](int m) { return sn(cont ? (n_iters - m) : (n_iters - 1 - m)); };
+  TRY((kd_adjoint_loop<M>(h, n_iters, Rm, dt, state, st)));
+  return kd_adjoint_finish<M>(h, Rm, dt, cont, gB, gU, st);
 }
 
-#define KD_DISPATCH(h, CALL)                                                                       \
+// ---- checkpointed sweeps (two-level, revolve style) -----------------------------------------------------------------
+// The forward solve keeps only the states 0, every, 2*every, ... and the final state N (slot ceil(N/every)); the adjoint
+// walks the segments backwards, recomputing the states of one segment into a buffer of every+1 slots before it sweeps
+// them.  Memory: ceil(N/every) + 1 + every + 1 states instead of N + 1; extra work: at most N - every forward steps
+// (recompute factor rho < 1 of one forward solve).
+static int ckpt_slots(int n_iters, int every) { return (n_iters + every - 1) / every + 1; }
+static int ckpt_slot_of(int n, int n_iters, int every) { return n == n_iters ? ckpt_slots(n_iters, every) - 1 : n / every; }
+struct CkptState {   // forward solve: checkpoints go to their slots, everything else to two scratch states
+  smo_kdyn* h; void* ck; int n_iters, every; cplx* cur[2][3]; int flip;
+  cplx* const* operator()(int n) {
+    if (n % every == 0 || n == n_iters) { flip ^= 1; snap_ptrs(h, ck, ckpt_slot_of(n, n_iters, every), cur[flip]); return cur[flip]; }
+    return (n & 1) ? h->NU : h->G;
+  }
+};
+template <int M> static int kd_forward_ckpt(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
+                                            int every, void* ck, double* J_host, rt_stream st) {
+  TRY(kd_set_U<M>(h, U, st));
+  cplx* s0[3];
+  snap_ptrs(h, ck, 0, s0);
+  TRY(KdOps<M>::to_coef(h, B0, s0, st));
+  CkptState state; state.h = h; state.ck = ck; state.n_iters = n_iters; state.every = every; state.flip = 0;
+  TRY((kd_forward_loop<M>(h, n_iters, Rm, dt, state, st)));
+  snap_ptrs(h, ck, ckpt_slot_of(n_iters, n_iters, every), s0);
+  TRY(KdOps<M>::to_grid(h, s0, h->gwork, st));
+  const double scale = 1.0 / ((double)M * M * M);
+  prof_collect(h, st);
+  return smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st);
+}
+template <int M> static int kd_adjoint_ckpt(smo_kdyn* h, double Rm, double dt, int n_iters, int every, const void* ckc, void* seg,
+                                            double* gB, double* gU, int flags, rt_stream st) {
+  const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
+  void* ck = const_cast<void*>(ckc);
+  cplx* s[3];
+  snap_ptrs(h, ck, ckpt_slot_of(n_iters, n_iters, every), s);
+  TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
+  for (int c = 0; c < 3; ++c) TRY(rt_memset(h->NU[c], 0, sizeof(cplx) * h->csize, st));
+  const int nseg = (n_iters + every - 1) / every;
+  for (int k = nseg - 1; k >= 0; --k) {
+    const int n0 = k * every, n1 = (n0 + every < n_iters) ? n0 + every : n_iters;   // the segment holds the states n0 .. n1
+    // states the sweep needs from this segment: n1-1 .. n0 (discrete) or n1 .. n0+1 (continuous)
+    const int steps = cont ? (n1 - n0) : (n1 - n0 - 1);            // forward steps to recompute from checkpoint n0
+    cplx* c0[3]; cplx* cur[2][3]; int flip = 0;
+    snap_ptrs(h, ck, k, c0);
+    auto segstate = [&](int j) -> cplx* const* {                    // state n0 + j
+      if (j == 0) return c0;
+      flip ^= 1; snap_ptrs(h, seg, j, cur[flip]); return cur[flip];
+    };
+    TRY((kd_forward_loop<M>(h, steps, Rm, dt, segstate, st)));
+    if (k != nseg - 1 && h->fused_z) TRY(KdOps<M>::curl_G(h, Rm, dt, st));   // W = curl G (the fused step keeps it on chip only)
+    auto sweep = [&](int i) -> cplx* const* { return segstate(cont ? (n1 - n0 - i) : (n1 - n0 - 1 - i)); };
+    TRY((kd_adjoint_loop<M>(h, n1 - n0, Rm, dt, sweep, st)));
+  }
+  return kd_adjoint_finish<M>(h, Rm, dt, cont, gB, gU, st);
+}
+
+#define KD_DISPATCH(h, CALL, ...)                                                                  \
   switch ((h)->M) {                                                                                \
-    case 24: return CALL<24>;                                                                      \
-    case 36: return CALL<36>;                                                                      \
-    case 48: return CALL<48>;                                                                      \
-    case 96: return CALL<96>;                                                                      \
-    case 192: return CALL<192>;                                                                    \
+    case 24: return CALL<24>(__VA_ARGS__);                                                         \
+    case 36: return CALL<36>(__VA_ARGS__);                                                         \
+    case 48: return CALL<48>(__VA_ARGS__);                                                         \
+    case 96: return CALL<96>(__VA_ARGS__);                                                         \
+    case 192: return CALL<192>(__VA_ARGS__);                                                       \
+    case 384: return CALL<384>(__VA_ARGS__);                                                       \
     default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", (h)->N);    \
   }
+template <int M> static int kd_to_coef(smo_kdyn* h, const double* grid, cplx* const* c, rt_stream st) { return KdOps<M>::to_coef(h, grid, c, st); }
+template <int M> static int kd_to_grid(smo_kdyn* h, const cplx* const* c, double* grid, rt_stream st) { return KdOps<M>::to_grid(h, c, grid, st); }
 
-static bool kd_supported(int Npts) { return Npts == 16 || Npts == 24 || Npts == 32 || Npts == 64 || Npts == 128; }
+static bool kd_supported(int Npts) { return Npts == 16 || Npts == 24 || Npts == 32 || Npts == 64 || Npts == 128 || Npts == 256; }
 
 extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, int nranks, void* comm) {
   if (!out) return fail(SMO_E_ARG, "smo_kdyn_create: null handle pointer");
-  if (!kd_supported(Npts)) return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported (16, 24, 32, 64, 128)", Npts);
+  if (!kd_supported(Npts)) return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported (16, 24, 32, 64, 128, 256)", Npts);
   if (!(L > 0) || nranks < 1 || rank < 0 || rank >= nranks) return fail(SMO_E_ARG, "smo_kdyn_create: bad L/rank/nranks");
   const int M = 3 * Npts / 2, Nh = Npts / 2;
   if (Nh % nranks || M % nranks) return fail(SMO_E_ARG, "nranks=%d must divide Npts/2=%d and 3*Npts/2=%d", nranks, Nh, M);
@@ -1085,29 +1157,14 @@ extern "C" int smo_kdyn_forward(smo_kdyn_t* h, const double* B0, const double* U
   TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward"));
   if (!B0 || !U || !snaps || !J_host) return fail(SMO_E_ARG, "smo_kdyn_forward: null buffer");
   rt_stream st = (rt_stream)stream;
-#define CALL_FWD kd_forward
-  switch (h->M) {
-    case 24: return kd_forward<24>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
-    case 36: return kd_forward<36>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
-    case 48: return kd_forward<48>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
-    case 96: return kd_forward<96>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
-    case 192: return kd_forward<192>(h, B0, U, Rm, dt, n_iters, snaps, J_host, st);
-    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
-  }
+  KD_DISPATCH(h, kd_forward, h, B0, U, Rm, dt, n_iters, snaps, J_host, st)
 }
 extern "C" int smo_kdyn_prep(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                              double* out, void* stream) {
   TRY(kd_args(h, Rm, dt, n_iters, 0, "smo_kdyn_prep"));
   if (!B0 || !U || !out) return fail(SMO_E_ARG, "smo_kdyn_prep: null buffer");
   rt_stream st = (rt_stream)stream;
-  switch (h->M) {
-    case 24: return kd_prep<24>(h, B0, U, Rm, dt, n_iters, out, st);
-    case 36: return kd_prep<36>(h, B0, U, Rm, dt, n_iters, out, st);
-    case 48: return kd_prep<48>(h, B0, U, Rm, dt, n_iters, out, st);
-    case 96: return kd_prep<96>(h, B0, U, Rm, dt, n_iters, out, st);
-    case 192: return kd_prep<192>(h, B0, U, Rm, dt, n_iters, out, st);
-    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
-  }
+  KD_DISPATCH(h, kd_prep, h, B0, U, Rm, dt, n_iters, out, st)
 }
 extern "C" int smo_kdyn_adjoint(smo_kdyn_t* h, double Rm, double dt, int n_iters, const void* snaps, double* gB,
                                 double* gU, int flags, void* stream) {
@@ -1115,40 +1172,37 @@ extern "C" int smo_kdyn_adjoint(smo_kdyn_t* h, double Rm, double dt, int n_iters
   if (!snaps || !gB || !gU) return fail(SMO_E_ARG, "smo_kdyn_adjoint: null buffer");
   if (!h->have_U) return fail(SMO_E_STATE, "smo_kdyn_adjoint: no preceding forward solve on this handle");
   rt_stream st = (rt_stream)stream;
-  switch (h->M) {
-    case 24: return kd_adjoint<24>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
-    case 36: return kd_adjoint<36>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
-    case 48: return kd_adjoint<48>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
-    case 96: return kd_adjoint<96>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
-    case 192: return kd_adjoint<192>(h, Rm, dt, n_iters, snaps, gB, gU, flags, st);
-    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
-  }
+  KD_DISPATCH(h, kd_adjoint, h, Rm, dt, n_iters, snaps, gB, gU, flags, st)
+}
+extern "C" size_t smo_kdyn_checkpoint_bytes(const smo_kdyn_t* h, int n_iters, int every) {
+  return (h && every > 0 && n_iters >= 0) ? sizeof(cplx) * 3 * h->csize * (size_t)ckpt_slots(n_iters, every) : 0;
+}
+extern "C" int smo_kdyn_forward_ckpt(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
+                                     int every, void* ckpt, double* J_host, int flags, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward_ckpt"));
+  if (!B0 || !U || !ckpt || !J_host || every < 1) return fail(SMO_E_ARG, "smo_kdyn_forward_ckpt: bad argument");
+  rt_stream st = (rt_stream)stream;
+  KD_DISPATCH(h, kd_forward_ckpt, h, B0, U, Rm, dt, n_iters, every, ckpt, J_host, st)
+}
+extern "C" int smo_kdyn_adjoint_ckpt(smo_kdyn_t* h, double Rm, double dt, int n_iters, int every, const void* ckpt, void* seg,
+                                     double* gB, double* gU, int flags, void* stream) {
+  TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_adjoint_ckpt"));
+  if (!ckpt || !seg || !gB || !gU || every < 1) return fail(SMO_E_ARG, "smo_kdyn_adjoint_ckpt: bad argument");
+  if (!h->have_U) return fail(SMO_E_STATE, "smo_kdyn_adjoint_ckpt: no preceding forward solve on this handle");
+  rt_stream st = (rt_stream)stream;
+  KD_DISPATCH(h, kd_adjoint_ckpt, h, Rm, dt, n_iters, every, ckpt, seg, gB, gU, flags, st)
 }
 extern "C" int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid, void* coef, void* stream) {
   if (!h || !grid || !coef) return fail(SMO_E_ARG, "smo_kdyn_to_coef: bad argument");
   rt_stream st = (rt_stream)stream;
   cplx* c[3] = {(cplx*)coef, (cplx*)coef + h->csize, (cplx*)coef + 2 * h->csize};
-  switch (h->M) {
-    case 24: return KdOps<24>::to_coef(h, grid, c, st);
-    case 36: return KdOps<36>::to_coef(h, grid, c, st);
-    case 48: return KdOps<48>::to_coef(h, grid, c, st);
-    case 96: return KdOps<96>::to_coef(h, grid, c, st);
-    case 192: return KdOps<192>::to_coef(h, grid, c, st);
-    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
-  }
+  KD_DISPATCH(h, kd_to_coef, h, grid, c, st)
 }
 extern "C" int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef, double* grid, void* stream) {
   if (!h || !grid || !coef) return fail(SMO_E_ARG, "smo_kdyn_to_grid: bad argument");
   rt_stream st = (rt_stream)stream;
   const cplx* c[3] = {(const cplx*)coef, (const cplx*)coef + h->csize, (const cplx*)coef + 2 * h->csize};
-  switch (h->M) {
-    case 24: return KdOps<24>::to_grid(h, c, grid, st);
-    case 36: return KdOps<36>::to_grid(h, c, grid, st);
-    case 48: return KdOps<48>::to_grid(h, c, grid, st);
-    case 96: return KdOps<96>::to_grid(h, c, grid, st);
-    case 192: return KdOps<192>::to_grid(h, c, grid, st);
-    default: return fail(SMO_E_UNSUPPORTED, "kinematic dynamo: Npts=%d not supported", h->N);
-  }
+  KD_DISPATCH(h, kd_to_grid, h, c, grid, st)
 }
 extern "C" int smo_kdyn_profile_set(smo_kdyn_t* h, int which) {
   if (!h) return fail(SMO_E_ARG, "smo_kdyn_profile_set: null handle");

@@ -46,7 +46,7 @@ template <class F, int T_, int MODE, int NFI, int NFO> struct XPass {
   static constexpr int R1 = F::R1, R2 = F::R2, M = F::M, RT = F::RT;
   static constexpr int THREADS = NJ * RT;
   static constexpr int NPHASES = (MODE == X_C2R) ? 2 : 8;
-  static constexpr int MIN_BLOCKS = SMO_X_MB;
+  static constexpr int MIN_BLOCKS = (F::RT > 16) ? 1 : SMO_X_MB;
   static constexpr int XLEN = (F::XP > FS::XP) ? ((F::XP > M) ? F::XP : M) : ((FS::XP > M) ? FS::XP : M);
   static constexpr size_t SMEM = (size_t)NJ * XLEN * sizeof(cplx);
   static_assert(T_ % 2 == 0, "columns are processed in pairs");
@@ -244,7 +244,7 @@ template <class F, int MODE> struct XFused {
   static constexpr int NARROW = HP * R2;             // active threads per field in the R2-thread stages
   static constexpr int THREADS = NF * FT;
   static constexpr int NPHASES = 9;
-  static constexpr int MIN_BLOCKS = (THREADS <= 96) ? 2 * SMO_X_MB : SMO_X_MB;
+  static constexpr int MIN_BLOCKS = (RT > 16) ? 1 : ((THREADS <= 96) ? 2 * SMO_X_MB : SMO_X_MB);
   static constexpr int XLEN = (F::XP > FS::XP) ? ((F::XP > M) ? F::XP : M) : ((FS::XP > M) ? FS::XP : M);
   static constexpr int XLP = XLEN + ((12 - XLEN % 8) % 8);   // pitch of one FFT's exchange region, = 4 (mod 8) 16-byte units
   static constexpr bool WSYNC = (FT == 32);

@@ -59,7 +59,7 @@ template <class F, int T_> struct ZStep {
   static constexpr int KMAX = M / 3 - 1, NC = 2 * KMAX + 1, PC = NC + 1;
   static constexpr int THREADS = 3 * T_ * F::RT;
   static constexpr int NPHASES = 9;
-  static constexpr int MIN_BLOCKS = SMO_ZS_MB;
+  static constexpr int MIN_BLOCKS = (F::RT > 16) ? 2 : SMO_ZS_MB;
   static constexpr bool WARP_OK = (32 % F::RT == 0);       // the RT threads of a line never straddle a warp
   static constexpr int LAND = 3 * T_ * M, WORK = 3 * T_ * XP;
   static constexpr size_t SMEM = (size_t)(LAND + WORK + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int);

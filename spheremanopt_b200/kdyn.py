@@ -168,8 +168,38 @@ class SnapshotStore(dict):
         return np.transpose(a.cpu().numpy(), (1, 2, 3, 0)).copy()
 
 
-def GEN_BUFFER(Npts, domain, N_SUB_ITERS):
-    """KD:319-355"""
+class CheckpointStore(dict):
+    """Two-level (revolve-style) checkpoint store for runs whose N_SUB_ITERS+1 states do not fit in HBM (BASELINE config 4:
+    256^3 x 1000 steps = 401 GB).  The forward solve keeps the states 0, every, 2*every, ... and the final one; the adjoint
+    sweep recomputes one segment of ``every`` states at a time.  ``rho`` = extra forward steps / N_ITERS (forward-recompute
+    factor quoted next to every checkpointed number); results are bit-identical to the fully stored sweep."""
+
+    def __init__(self, domain, n_iters, every):
+        super().__init__()
+        self.domain, self.n_iters, self.every = domain, int(n_iters), int(every)
+        lib = domain.lib
+        self.buf = torch.zeros(lib.smo_kdyn_checkpoint_bytes(domain.h, self.n_iters, self.every) // 16, dtype=torch.complex128,
+                               device=domain.device)
+        self.seg = torch.zeros(lib.smo_kdyn_snapshot_bytes(domain.h, self.every) // 16, dtype=torch.complex128, device=domain.device)
+        self.valid = False
+        nseg = (self.n_iters + self.every - 1) // self.every
+        self.states_held = nseg + 1 + self.every + 1
+        self.rho = sum(max(min(self.every, self.n_iters - k * self.every) - 1, 0) for k in range(nseg)) / max(self.n_iters, 1)
+
+    def ptr(self):
+        return self.buf.data_ptr()
+
+
+def GEN_BUFFER(Npts, domain, N_SUB_ITERS, checkpoint_every=None):
+    """KD:319-355.  ``checkpoint_every``: None = keep every state in HBM if it fits (else sqrt(N)-spaced checkpoints),
+    0 = always keep every state, k > 0 = checkpoint every k-th state (CheckpointStore)."""
+    if checkpoint_every is None:
+        need = domain.lib.smo_kdyn_snapshot_bytes(domain.h, int(N_SUB_ITERS))
+        with torch.cuda.device(domain.device):
+            free, _ = torch.cuda.mem_get_info()
+        checkpoint_every = 0 if need < 0.8 * free else int(np.ceil(np.sqrt(max(int(N_SUB_ITERS), 1))))
+    if checkpoint_every and checkpoint_every > 0:
+        return CheckpointStore(domain, N_SUB_ITERS, checkpoint_every)
     return SnapshotStore(domain, N_SUB_ITERS)
 
 
@@ -222,9 +252,14 @@ def FWD_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost
     Bt, Ut = _as_slab(domain, X0[0]), _as_slab(domain, X0[1])
     J = C.c_double()
     with torch.cuda.device(domain.device):
-        _cabi.check(domain.lib, domain.lib.smo_kdyn_forward(domain.h, Bt.data_ptr(), Ut.data_ptr(), float(Rm), float(dt),
-                                                            int(N_ITERS), X_FWD_DICT.ptr(), C.byref(J),
-                                                            _flags(Cost_function, "Discrete"), _stream_ptr()))
+        if isinstance(X_FWD_DICT, CheckpointStore):
+            _cabi.check(domain.lib, domain.lib.smo_kdyn_forward_ckpt(domain.h, Bt.data_ptr(), Ut.data_ptr(), float(Rm), float(dt),
+                                                                     int(N_ITERS), X_FWD_DICT.every, X_FWD_DICT.ptr(), C.byref(J),
+                                                                     _flags(Cost_function, "Discrete"), _stream_ptr()))
+        else:
+            _cabi.check(domain.lib, domain.lib.smo_kdyn_forward(domain.h, Bt.data_ptr(), Ut.data_ptr(), float(Rm), float(dt),
+                                                                int(N_ITERS), X_FWD_DICT.ptr(), C.byref(J),
+                                                                _flags(Cost_function, "Discrete"), _stream_ptr()))
     X_FWD_DICT.valid = True
     return (-1.) * domain.allreduce_sum(J.value)
 
@@ -236,9 +271,14 @@ def ADJ_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost
     gB = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
     gU = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
     with torch.cuda.device(domain.device):
-        _cabi.check(domain.lib, domain.lib.smo_kdyn_adjoint(domain.h, float(Rm), float(dt), int(N_ITERS), X_FWD_DICT.ptr(),
-                                                            gB.data_ptr(), gU.data_ptr(),
-                                                            _flags(Cost_function, Adjoint_type), _stream_ptr()))
+        if isinstance(X_FWD_DICT, CheckpointStore):
+            _cabi.check(domain.lib, domain.lib.smo_kdyn_adjoint_ckpt(domain.h, float(Rm), float(dt), int(N_ITERS), X_FWD_DICT.every,
+                                                                     X_FWD_DICT.ptr(), X_FWD_DICT.seg.data_ptr(), gB.data_ptr(),
+                                                                     gU.data_ptr(), _flags(Cost_function, Adjoint_type), _stream_ptr()))
+        else:
+            _cabi.check(domain.lib, domain.lib.smo_kdyn_adjoint(domain.h, float(Rm), float(dt), int(N_ITERS), X_FWD_DICT.ptr(),
+                                                                gB.data_ptr(), gU.data_ptr(),
+                                                                _flags(Cost_function, Adjoint_type), _stream_ptr()))
     return [_wrap_like(domain, X0[0], gB), _wrap_like(domain, X0[1], gU)]
 
 

@@ -88,6 +88,31 @@ def test_kdyn_emulated(L, Npts, nit):
     L.smo_kdyn_destroy(h)
 
 
+@pytest.mark.parametrize("every,cont", [(1, 0), (3, 0), (4, 1), (7, 0), (16, 1)])
+def test_kdyn_checkpointed_emulated(L, every, cont):
+    """two-level checkpointing must reproduce the fully stored sweep bit for bit (same kernels, same order)"""
+    Npts, nit = 16, 7
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    emul.check(L.smo_kdyn_create(C.byref(h), Npts, od.L, 0, 1, None))
+    gsz = L.smo_kdyn_grid_elems(h)
+    Rm, dt = 2.0, 1e-3
+    snaps = np.zeros(L.smo_kdyn_snapshot_bytes(h, nit) // 16, dtype=complex)
+    J = C.c_double(); Jc = C.c_double()
+    emul.check(L.smo_kdyn_forward(h, emul.ptr(B0), emul.ptr(U), Rm, dt, nit, emul.ptr(snaps), C.byref(J), 0, None))
+    gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
+    emul.check(L.smo_kdyn_adjoint(h, Rm, dt, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), cont, None))
+    ck = np.zeros(L.smo_kdyn_checkpoint_bytes(h, nit, every) // 16, dtype=complex)
+    seg = np.zeros(L.smo_kdyn_snapshot_bytes(h, every) // 16, dtype=complex)
+    emul.check(L.smo_kdyn_forward_ckpt(h, emul.ptr(B0), emul.ptr(U), Rm, dt, nit, every, emul.ptr(ck), C.byref(Jc), 0, None))
+    gBc, gUc = np.zeros(3 * gsz), np.zeros(3 * gsz)
+    emul.check(L.smo_kdyn_adjoint_ckpt(h, Rm, dt, nit, every, emul.ptr(ck), emul.ptr(seg), emul.ptr(gBc), emul.ptr(gUc), cont, None))
+    assert Jc.value == J.value
+    assert np.array_equal(gBc, gB) and np.array_equal(gUc, gU)
+    L.smo_kdyn_destroy(h)
+
+
 def test_vector_kernels_emulated(L):
     od = okd.domain_kdyn(16)
     n = 3 * od.M ** 3

@@ -83,6 +83,49 @@ def test_kdyn_f_gradf(Npts, nit):
     assert abs(ip - ipo) <= TOL * abs(ipo)
 
 
+@pytest.mark.parametrize("Npts,nit", [(128, 2), (256, 1)])
+def test_kdyn_large_grids(Npts, nit):
+    """BASELINE configs 3 and 4 at their full grid sizes (few steps: the oracle needs ~1 s per 3-D transform)"""
+    from spheremanopt_b200 import kdyn
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    B0 = kdyn_field(od, 1)
+    U = kdyn_field(od, 2)
+    Rm, dt = 10.0, 1e-3
+    store = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=0)
+    f = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, store)
+    g = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, store)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    assert abs(f - fo) <= TOL * abs(fo)
+    assert relerr(g[0], go[0]) <= TOL
+    assert relerr(g[1], go[1]) <= TOL
+
+
+@pytest.mark.parametrize("every,adj", [(1, "Discrete"), (4, "Discrete"), (5, "Continuous"), (64, "Discrete")])
+def test_kdyn_checkpointed_sweep(every, adj):
+    """revolve-style two-level checkpointing (config 4): bit-identical to the fully stored sweep, and equal to the oracle"""
+    from spheremanopt_b200 import kdyn
+    Npts, nit = 24, 13
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    Rm, dt = 1.0, 1e-3
+    full = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=0)
+    f = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, full, "Final", adj)
+    g = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, full, "Final", adj)
+    ck = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=every)
+    assert isinstance(ck, kdyn.CheckpointStore) and ck.states_held <= (nit + every - 1) // every + every + 2
+    fc = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, ck, "Final", adj)
+    gc = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, ck, "Final", adj)
+    assert fc == f and np.array_equal(gc[0], g[0]) and np.array_equal(gc[1], g[1])
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D, "Final", adj)
+    assert abs(fc - fo) <= TOL * abs(fo) and relerr(gc[0], go[0]) <= TOL and relerr(gc[1], go[1]) <= TOL
+
+
 def test_kdyn_non_solenoidal_input():
     """adversarial input (not band-limited, not divergence free, non-zero mean): exercises the truncation on first
     gather, the projection of the parameter field U [D2-8] and the k.B carry of the closed-form CNAB1 pencil"""
