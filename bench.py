@@ -37,7 +37,12 @@ WORKLOADS = {
     "kdyn128": (128, 10.0, 1e-3, 1000),
     "kdyn64": (64, 10.0, 1e-3, 1000),
     "kdyn24": (24, 1.0, 1e-3, 1000),
+    # BASELINE config 5: 4096 independent SH23 problems (Npts=256, dt=0.1, T=50), M_0 swept over [0.05, 0.1], sharded over the GPUs
+    "sh23ens": (256, None, 0.1, 500),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
+# (profiles/r1f_kdyn128_adj_step_ncu.txt: 396.4 MB read + 177.9 MB written; algorithmic 566.2 MB)
+NCU_TRAFFIC = {("kdyn128", 1): 574.3e6}
 METRIC = "Grad_f evals/s (fwd+adjoint)"
 UNIT = "Grad_f evals/s"
 
@@ -150,6 +155,20 @@ def run_reference(args):
     if rank != 0:
         return
     N, Rm, dt, nit = WORKLOADS[args.workload]
+    if args.workload == "sh23ens":
+        from oracle import sh23 as osh
+        od, X0 = osh.Generate_IC(0.0725)
+        D = osh.GEN_BUFFER(od, nit)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            osh.FWD_Solve_IVP_Lin([X0], od, dt, nit, nit, D); osh.ADJ_Solve_IVP_Lin([X0], od, dt, nit, nit, D)
+        value = 2.0 / (time.perf_counter() - t0)
+        info = {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": "numpy oracle, 2 of 4096 instances, serial"}
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 4096e3 / value, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": "SH23 ensemble (config 5), oracle sample"},
+                          "cpu_baseline": info, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     sample_steps = {128: 2, 64: 8, 24: 100}.get(N, 2)
     vals = []
     info = None
@@ -299,7 +318,8 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "XPass<X_ADJ> (fused c2r + (curl G)xU, (curl G)xB_f + r2c, adjoint step)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                         "traffic": NCU_TRAFFIC.get((args.workload, world)),
                          "launch_ms": k_ms, "launches_timed": int(kn.value), "share_of_step": kms.value / (ms_step * args.steps),
                          "algorithmic_bytes_per_launch": k_alg, "peak_source": peak_src},
             "roofline_pair": {"bound": "hbm", "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak,
@@ -316,6 +336,98 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_gpu_sh23ens(args):
+    """config 5: one step = f + Grad_f of the whole ensemble (4096 instances, one kernel launch each way per GPU)"""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from spheremanopt_b200 import _cabi, sh23
+    lib = _cabi.load()
+    N, _, dt, nit = WORKLOADS["sh23ens"]
+    total = 4096
+    nb = total // world
+    dom, X0 = sh23.Generate_IC(0.0725, N, device="cuda:%d" % local)
+    M0 = np.linspace(0.05, 0.1, total)[rank * nb:(rank + 1) * nb]
+    X = torch.from_numpy(np.sqrt(M0 / 0.0725)[:, None] * X0[None, :]).to(dom.device).reshape(-1).contiguous()
+    store = sh23.GEN_BUFFER(dom, nit, N, batch=nb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def pair(x):
+        J = sh23.forward_batch(x, dom, dt, nit, store)
+        G = sh23.adjoint_batch(dom, dt, nit, store)
+        return J, G
+    for _ in range(args.warmup):
+        pair(X)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = lib.smo_launch_count()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    tf = ta = 0.0
+    for _ in range(args.steps):
+        e[1].record(); J = sh23.forward_batch(X, dom, dt, nit, store)
+        e[2].record(); G = sh23.adjoint_batch(dom, dt, nit, store)
+        e[3].record()
+    e3 = torch.cuda.Event(enable_timing=True); e3.record()
+    barrier()
+    launches = lib.smo_launch_count() - n0
+    ms_total = e[0].elapsed_time(e3)
+    t_adj = e[2].elapsed_time(e[3])     # last adjoint launch (the dominant kernel)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dom.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = total / (ms_step * 1e-3)
+    # e2e: pinned host vectors in, host gradients + J out
+    Xh = torch.empty(nb * dom.M, dtype=torch.float64, pin_memory=True); Xh.copy_(X.cpu())
+    Gh = torch.empty(nb * dom.M, dtype=torch.float64, pin_memory=True)
+    barrier(); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Xd = Xh.to(dom.device, non_blocking=True)
+        J, G = pair(Xd)
+        Gh.copy_(G, non_blocking=True); Jh = J.cpu()
+    barrier(); t1 = time.perf_counter()
+    te = torch.tensor([(t1 - t0) / args.steps], dtype=torch.float64, device=dom.device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    alg_inst = 2 * (nit + 1) * (N // 2) * 16 + 2 * 2 * N * 8          # snapshots written + read, X in, gradient out
+    alg_adj = nb * ((nit + 1) * (N // 2) * 16 + 2 * N * 8)
+    ach = alg_adj / (t_adj * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "SH23 ensemble: %d independent problems Npts=%d (grid %d), dt=%g, N_ITERS=%d, M_0 in [0.05,0.1], discrete adjoint; "
+                                   "one step = f + Grad_f of every instance; sharded %d per GPU, no collective" % (total, N, 2 * N, dt, nit, nb),
+                       "instances": total, "Npts": N, "N_ITERS": nit, "dof": N,
+                       "cache": "snapshot store %.1f GB per GPU streams through HBM; the state of an instance lives in shared memory" % (nb * (nit + 1) * (N // 2) * 16 / 1e9)},
+            "dof_steps_per_s": N * 2 * nit * value,
+            "e2e": {"value": total / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": nb * dom.M * 8 * world, "d2h_bytes_per_step": (nb * dom.M * 8 + nb * 8) * world},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "Sh23Adj (whole adjoint time loop of %d instances, one launch)" % nb, "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "launch_ms": t_adj, "algorithmic_bytes_per_launch": alg_adj,
+                         "peak_source": peak_src,
+                         "note": "serial fp64 chain per instance: the fp64 pipe and shared memory bind, not HBM (SURVEY 8(d)); %d B algorithmic per instance pair" % alg_inst}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -327,6 +439,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sh23ens":
+        run_gpu_sh23ens(args)
     else:
         run_gpu(args)
 
