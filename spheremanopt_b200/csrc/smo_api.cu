@@ -439,6 +439,9 @@ struct smo_kdyn {
   size_t ev_used;
 #endif
   int use_graph;
+  // CUDA-graph replay of the time loops (launch-gap bound small grids / many GPUs): cache of instantiated graphs
+  struct GraphCache* graphs;
+  int capturing; unsigned long long cap_a0, cap_b0; unsigned long long* epoch_dev;
   // peer-memory transposes (CUDA IPC): pointers to every rank's p1 / p1t buffers and flag words
   int peer_on;
   cplx* peer_p1[MAXF][MAXP]; cplx* peer_p1t[MAXF][MAXP];
@@ -459,11 +462,14 @@ static void prof_begin(smo_kdyn* h, int kind, rt_stream st) {
   if (h->ev_used + 2 > h->ev->size()) {
     for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev->push_back(e); }
   }
-  cudaEventRecord((*h->ev)[h->ev_used], st);
+  // inside a stream capture the record must become a graph node of its own (external event), re-recorded by every replay
+  if (h->capturing) cudaEventRecordWithFlags((*h->ev)[h->ev_used], st, cudaEventRecordExternal);
+  else cudaEventRecord((*h->ev)[h->ev_used], st);
 }
 static void prof_end(smo_kdyn* h, int kind, rt_stream st) {
   if (h->prof_which != kind) return;
-  cudaEventRecord((*h->ev)[h->ev_used + 1], st);
+  if (h->capturing) cudaEventRecordWithFlags((*h->ev)[h->ev_used + 1], st, cudaEventRecordExternal);
+  else cudaEventRecord((*h->ev)[h->ev_used + 1], st);
   h->ev_used += 2;
 }
 static void prof_collect(smo_kdyn* h, rt_stream st) {
@@ -472,6 +478,7 @@ static void prof_collect(smo_kdyn* h, rt_stream st) {
   for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, (*h->ev)[i], (*h->ev)[i + 1]) == cudaSuccess) { h->prof_ms += ms; h->prof_n++; }
+    else (void)cudaGetLastError();   // do not leave a stale error for the next launch check
   }
   h->ev_used = 0;
 }
@@ -561,6 +568,19 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 #ifndef SMO_TZS
 #define SMO_TZS 2
 #endif
+// ---- CUDA graphs ----------------------------------------------------------------------------------------------
+struct GraphKey {
+  int kind, n, opts; const void* p0; const void* p1; double Rm, dt;
+  bool operator==(const GraphKey& o) const { return kind == o.kind && n == o.n && opts == o.opts && p0 == o.p0 && p1 == o.p1 && Rm == o.Rm && dt == o.dt; }
+};
+#if !defined(SMO_EMUL)
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; unsigned long long nA, nB; long long nlaunch; size_t ev0, ev1; };
+struct GraphCache { std::vector<GraphEntry> e; cudaStream_t stream; cudaEvent_t ev0, ev1; };
+__global__ void set_epoch_base_kernel(unsigned long long* dev, unsigned long long a, unsigned long long b) { dev[1] = a; dev[2] = b; }
+#else
+struct GraphCache { int unused; };
+#endif
+
 // ---- in-kernel hand-shakes ----------------------------------------------------------------------------------
 enum { XS_NONE = 0, XS_A = 1, XS_B = 2 };
 static bool kernel_sync(const smo_kdyn* h) { return h->peer_on && h->inkernel_sync; }
@@ -569,6 +589,7 @@ static void xs_signal(smo_kdyn* h, XSync& xs, int which) {
   if (which == XS_NONE || !kernel_sync(h)) return;
   xs.sig_n = h->nranks; xs.sig_rank = h->rank; xs.sig_sys = h->peer_pull ? 0 : 1;
   xs.sig_epoch = (which == XS_A) ? ++h->epochA : ++h->epochB;
+  if (h->capturing) { xs.sig_epoch -= (which == XS_A) ? h->cap_a0 : h->cap_b0; xs.sig_base = h->epoch_dev + which; }
   for (int s = 0; s < h->nranks; ++s) xs.sig_flags[s] = h->peer_flags[s] + which * MAXP;
   xs.counter = h->counters + which;
 }
@@ -577,6 +598,7 @@ static void xs_wait(smo_kdyn* h, XSync& xs, int which) {
   if (which == XS_NONE || !kernel_sync(h)) return;
   xs.wait_flags = h->flags + which * MAXP; xs.wait_n = h->nranks;
   xs.wait_epoch = (which == XS_A) ? h->epochA : h->epochB;
+  if (h->capturing) { xs.wait_epoch -= (which == XS_A) ? h->cap_a0 : h->cap_b0; xs.wait_base = h->epoch_dev + which; }
 }
 
 // ---- pass launchers ---------------------------------------------------------------------------------------
@@ -872,6 +894,66 @@ static void snap_ptrs(smo_kdyn* h, void* snaps, int n, cplx** out) {
   for (int c = 0; c < 3; ++c) out[c] = s + ((size_t)n * 3 + c) * h->csize;
 }
 
+// Runs body(stream) - a fixed sequence of kernel launches - eagerly, or (smo_kdyn_use_graph) replays it from a cached CUDA
+// graph: the first call with a given key runs eagerly, the second one captures and instantiates, later ones only launch.
+template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, rt_stream st, Body body) {
+#if defined(SMO_EMUL)
+  (void)h; (void)key;
+  return body(st);
+#else
+  // (per-kernel profiling events are captured as event-record nodes: every replay re-records the same events)
+  const bool can = h->use_graph && h->fused_z && (h->nranks == 1 || kernel_sync(h));
+  if (!can) return body(st);
+  if (!h->graphs) {
+    h->graphs = new GraphCache();
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->graphs->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->graphs->ev0, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->graphs->ev1, cudaEventDisableTiming));
+    TRY(rt_malloc((void**)&h->epoch_dev, sizeof(unsigned long long) * 4));
+  }
+  GraphCache* gc = h->graphs;
+  GraphEntry* en = nullptr;
+  for (GraphEntry& e : gc->e) if (e.key == key) { en = &e; break; }
+  if (!en) {   // first sight: eager (also instantiates every kernel's launch configuration outside a capture)
+    if (gc->e.size() >= 64) { if (gc->e.front().exec) cudaGraphExecDestroy(gc->e.front().exec); gc->e.erase(gc->e.begin()); }
+    GraphEntry e; e.key = key; e.exec = nullptr; e.nA = e.nB = 0; e.nlaunch = 0; e.ev0 = e.ev1 = 0;
+    gc->e.push_back(e);
+    return body(st);
+  }
+  if (!en->exec) {
+    const unsigned long long a0 = h->epochA, b0 = h->epochB;
+    const long long l0 = g_launches.load();
+    en->ev0 = h->ev_used;
+    h->capturing = 1; h->cap_a0 = a0; h->cap_b0 = b0;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(gc->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(gc->stream);
+    const cudaError_t ce = cudaStreamEndCapture(gc->stream, &graph);
+    h->capturing = 0;
+    en->nA = h->epochA - a0; en->nB = h->epochB - b0; en->nlaunch = g_launches.load() - l0;
+    h->epochA = a0; h->epochB = b0; g_launches -= en->nlaunch;
+    en->ev1 = h->ev_used; h->ev_used = en->ev0;
+    if (rc != 0 || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc ? rc : fail(SMO_E_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&en->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { en->exec = nullptr; return fail(SMO_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+  }
+  if (h->ev_used != en->ev0) return body(st);   // the profiling events baked into this graph are in use: run eagerly
+  CUDA_TRY(cudaEventRecord(gc->ev0, st));
+  CUDA_TRY(cudaStreamWaitEvent(gc->stream, gc->ev0, 0));
+  if (h->nranks > 1) set_epoch_base_kernel<<<1, 1, 0, gc->stream>>>(h->epoch_dev, h->epochA, h->epochB);
+  CUDA_TRY(cudaGraphLaunch(en->exec, gc->stream));
+  CUDA_TRY(cudaEventRecord(gc->ev1, gc->stream));
+  CUDA_TRY(cudaStreamWaitEvent(st, gc->ev1, 0));
+  h->epochA += en->nA; h->epochB += en->nB; g_launches += en->nlaunch; h->ev_used = en->ev1;
+  return 0;
+#endif
+}
+static int graph_opts(const smo_kdyn* h) { return (h->prof_which << 24) | (h->fused_z ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16); }
+
 // loop bodies, templated on M ---------------------------------------------------------------------------------
 template <int M> static int kd_set_U(smo_kdyn* h, const double* U, rt_stream st) {
   // parameter fields are projected on the retained modes at first use [D2-8]: to_coef then to_grid
@@ -897,16 +979,19 @@ static int kd_forward_loop(smo_kdyn* h, int n_steps, double Rm, double dt, State
   // kernels (ks: producer signals at its end, consumer waits at its start) or separate barrier launches (a2a)
   const bool ks = kernel_sync(h);
   if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));     // every rank has left whatever used the pencil buffers before
-  TRY(KdOps<M>::inv_z(h, state(0), h->p1, 3, st, XS_B));
-  if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, st));
-  for (int n = 0; n < n_steps; ++n) {
-    TRY(KdOps<M>::yxy(h, 3, st));
-    if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, st));
-    const bool more = n + 1 < n_steps;
-    TRY(KdOps<M>::zstep(h, 0, state(n), state(n + 1), nullptr, more, Rm, dt, st));
-    if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 3, st));
-  }
-  return 0;
+  GraphKey key; key.kind = 1; key.n = n_steps; key.opts = graph_opts(h); key.p0 = state(0)[0]; key.p1 = state(n_steps)[0]; key.Rm = Rm; key.dt = dt;
+  return run_graphed(h, key, st, [&](rt_stream s) -> int {
+    TRY(KdOps<M>::inv_z(h, state(0), h->p1, 3, s, XS_B));
+    if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, s));
+    for (int n = 0; n < n_steps; ++n) {
+      TRY(KdOps<M>::yxy(h, 3, s));
+      if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, s));
+      const bool more = n + 1 < n_steps;
+      TRY(KdOps<M>::zstep(h, 0, state(n), state(n + 1), nullptr, more, Rm, dt, s));
+      if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 3, s));
+    }
+    return 0;
+  });
 }
 struct SnapState {
   smo_kdyn* h; void* snaps; cplx* cur[2][3]; int flip;
@@ -950,20 +1035,23 @@ static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn
     for (int i = 0; i < count; ++i) TRY(KdOps<M>::adj_step(h, state(i), Rm, dt, 0, st));
     return 0;
   }
-  cplx* const* s = state(0);
-  const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], s[0], s[1], s[2]};
   const bool ks = kernel_sync(h);
   if (ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
-  TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, st, XS_B));
-  if (!ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
-  for (int i = 0; i < count; ++i) {
-    TRY(KdOps<M>::yxy(h, 6, st));
-    if (!ks) TRY(a2a(h, h->p1t, h->p1, 6, st));
-    const bool more = i + 1 < count;
-    TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more ? state(i + 1) : nullptr, more, Rm, dt, st));
-    if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
-  }
-  return 0;
+  GraphKey key; key.kind = 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0)[0]; key.p1 = state(count - 1)[0]; key.Rm = Rm; key.dt = dt;
+  return run_graphed(h, key, st, [&](rt_stream q) -> int {
+    cplx* const* s = state(0);
+    const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], s[0], s[1], s[2]};
+    TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, q, XS_B));
+    if (!ks) TRY(a2a(h, h->p1, h->p1t, 6, q));
+    for (int i = 0; i < count; ++i) {
+      TRY(KdOps<M>::yxy(h, 6, q));
+      if (!ks) TRY(a2a(h, h->p1t, h->p1, 6, q));
+      const bool more = i + 1 < count;
+      TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more ? state(i + 1) : nullptr, more, Rm, dt, q));
+      if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 6, q));
+    }
+    return 0;
+  });
 }
 template <int M> static int kd_adjoint_finish(smo_kdyn* h, double Rm, double dt, int cont, double* gB, double* gU, rt_stream st) {
   TRY(KdOps<M>::final_scale(h, Rm, dt, cont, st));
@@ -1077,6 +1165,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->comm = comm;
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
+  h->graphs = nullptr; h->capturing = 0; h->cap_a0 = h->cap_b0 = 0; h->epoch_dev = nullptr;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
   h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0;
   for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
@@ -1132,7 +1221,12 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
       cudaIpcCloseMemHandle(h->peer_flags[s]);
     }
   }
-  rt_free(h->flags); rt_free(h->counters);
+  rt_free(h->flags); rt_free(h->counters); rt_free(h->epoch_dev);
+  if (h->graphs) {
+    for (GraphEntry& e : h->graphs->e) if (e.exec) cudaGraphExecDestroy(e.exec);
+    cudaStreamDestroy(h->graphs->stream); cudaEventDestroy(h->graphs->ev0); cudaEventDestroy(h->graphs->ev1);
+    delete h->graphs;
+  }
 #endif
   rt_free(h->hB); rt_free(h->hU); rt_free(h->hGB); rt_free(h->hGU); rt_free(h->snaps);
 #if !defined(SMO_EMUL)

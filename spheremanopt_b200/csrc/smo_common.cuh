@@ -83,11 +83,15 @@ template <int N> SMO_HD void cp_async_wait() {
 // +3.4 us (stores in flight); so the waiting side uses no fence at all - its loads are issued after the spin and a CTA
 // barrier, bypass L1 (cp.async.cg / peer addresses) and find the data already in the owning GPU's L2.
 // One process per GPU; the waiting kernel only ever waits for kernels running on OTHER GPUs.
+// Epochs are `*base + offset` when `base` is set (launches replayed from a CUDA graph: the offsets are baked into the
+// graph, the base is bumped before every replay), else plain values.
 struct XSync {
   const unsigned long long* wait_flags;   // local flag words, one per source rank; nullptr: no wait
+  const unsigned long long* wait_base;
   unsigned long long wait_epoch;
   int wait_n;
   int sig_n, sig_rank, sig_sys;           // sig_n = 0: no signal
+  const unsigned long long* sig_base;
   unsigned long long sig_epoch;
   unsigned long long* sig_flags[MAXP];    // the peers' flag arrays
   unsigned int* counter;                  // local: CTAs of this launch that have finished
@@ -154,7 +158,8 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
     if (p.xs.wait_flags != nullptr) {
       if ((int)threadIdx.x < p.xs.wait_n) {
         const volatile unsigned long long* f = p.xs.wait_flags + threadIdx.x;
-        while (*f < p.xs.wait_epoch) { /* spin: the peer's kernel runs on another GPU */ }
+        const unsigned long long want = p.xs.wait_epoch + (p.xs.wait_base ? *p.xs.wait_base : 0ull);
+        while (*f < want) { /* spin: the peer's kernel runs on another GPU */ }
       }
       __syncthreads();
     }
@@ -177,8 +182,9 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
         if (old == gridDim.x - 1) {
           *p.xs.counter = 0u;   // ready for the next launch
           __threadfence();
+          const unsigned long long val = p.xs.sig_epoch + (p.xs.sig_base ? *p.xs.sig_base : 0ull);
           for (int s = 0; s < p.xs.sig_n; ++s)
-            *((volatile unsigned long long*)(p.xs.sig_flags[s] + p.xs.sig_rank)) = p.xs.sig_epoch;
+            *((volatile unsigned long long*)(p.xs.sig_flags[s] + p.xs.sig_rank)) = val;
         }
       }
     }

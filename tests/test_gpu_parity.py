@@ -126,6 +126,30 @@ def test_kdyn_checkpointed_sweep(every, adj):
     assert abs(fc - fo) <= TOL * abs(fo) and relerr(gc[0], go[0]) <= TOL and relerr(gc[1], go[1]) <= TOL
 
 
+def test_kdyn_graph_replay():
+    """CUDA-graph replay of the time loops (eager first call, capture on the second, replay afterwards) changes nothing"""
+    from spheremanopt_b200 import kdyn
+    Npts, nit = 24, 9
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    store = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=0)
+    f0 = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, store)
+    g0 = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, store)
+    dom.lib.smo_kdyn_use_graph(dom.h, 1)
+    for rep in range(4):
+        scale = 1.0 + 0.25 * rep     # different inputs through the same graph: nothing but pointers is baked in
+        f = kdyn.FWD_Solve_IVP_Lin([scale * B0, U], dom, 1.0, 1e-3, nit, nit, store)
+        g = kdyn.ADJ_Solve_IVP_Lin([scale * B0, U], dom, 1.0, 1e-3, nit, nit, store)
+        assert abs(f - scale ** 2 * f0) <= 1e-12 * abs(f0) * scale ** 2
+        assert relerr(g[0], scale * g0[0]) <= 1e-12 and relerr(g[1], scale ** 2 * g0[1]) <= 1e-12
+    ck = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=4)
+    for rep in range(3):
+        fc = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, ck)
+        gc = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, ck)
+        assert fc == f0 and np.array_equal(gc[0], g0[0]) and np.array_equal(gc[1], g0[1])
+
+
 def test_kdyn_non_solenoidal_input():
     """adversarial input (not band-limited, not divergence free, non-zero mean): exercises the truncation on first
     gather, the projection of the parameter field U [D2-8] and the k.B carry of the closed-form CNAB1 pencil"""

@@ -33,9 +33,12 @@ C_ = (N // 2) * (N - 1) ** 2 * 16; P1 = (N // 2) * (N - 1) * M * 16; P2 = (N // 
 alg_f = 9 * C_ + 12 * P1 + 15 * P2; alg_a = 18 * C_ + 24 * P1 + 27 * P2
 import os
 chunk_sets = [tuple(int(v) for v in cs.split(",")) for cs in os.environ.get("CHUNKS", "1,1").split(";")]
+if os.environ.get("GRAPH"):
+    lib.smo_kdyn_use_graph(dom.h, 1)
 if os.environ.get("FUSED_Z") is not None:
     lib.smo_kdyn_set_option(dom.h, 1, int(os.environ["FUSED_Z"]))
-kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)   # warm-up (lazy module loading)
+for _ in range(3):
+    kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)   # warm-up (lazy module loading, graph capture)
 for cf, ca in chunk_sets:
   lib.smo_kdyn_set_chunks(dom.h, cf, ca)
   print("chunks fwd/adj:", cf, ca)

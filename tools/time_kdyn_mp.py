@@ -36,7 +36,10 @@ names = {0: "total", 1: "z-pass", 2: "y-pass", 3: "x-fwd", 5: "a2a", 6: "x-adj",
 for k, v in os.environ.items():
     if k.startswith("SMO_OPT_"):
         lib.smo_kdyn_set_option(dom.h, int(k[8:]), int(v))
-kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)
+if os.environ.get("GRAPH"):
+    lib.smo_kdyn_use_graph(dom.h, 1)
+for _ in range(3):
+    kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)
 def sync():
     torch.cuda.synchronize()
     if world > 1:
