@@ -31,6 +31,7 @@ struct Sh23Params {
   int nwork, nsteps;
   int batch, n_iters, Nh;
   double dt, a, kfac;    // kfac = 2 pi / L
+  double inv_dt;         // 1/dt (set by the host: the time loop itself contains no fp64 division)
   int flags;             // bit0: continuous adjoint; bit1: prep mode; bit2: initial state given as coefficients
   const cplx* cin;       // [batch][Nh] initial coefficients (bit2)
   const cplx* twH;       // exp(-2 pi i m / H)
@@ -40,7 +41,7 @@ struct Sh23Params {
 SMO_HD double sh_A(const Sh23Params& p, int k) {
   const double kk = p.kfac * (double)k;
   const double t = 1.0 - kk * kk;
-  return 1.0 / p.dt + t * t - p.a;
+  return p.inv_dt + t * t - p.a;
 }
 
 template <class F> struct Sh23Core {
@@ -128,8 +129,10 @@ template <class F, int NI_> struct Sh23Fwd {
   static constexpr int THREADS = NI_ * RT;
   static constexpr int NPHASES = 4;
   static constexpr int MIN_BLOCKS = 1;
-  static constexpr int PER_INST = Cr::NHMAX + 2 * Cr::XLEN;   // C | XA | XB
+  static constexpr int PER_INST = Cr::NHMAX + 2 * Cr::XLEN + Cr::NHMAX / 2;   // C | XA | XB | 1/A_k (doubles)
   static constexpr size_t SMEM = (size_t)NI_ * PER_INST * sizeof(cplx);
+  // an instance is private to its RT threads: with RT dividing 32 every barrier of the time loop is a __syncwarp
+  SMO_HD static constexpr int sync_after(int) { return (32 % RT == 0) ? 1 : 2; }
   struct State {
     double re[RT], im[RT];
     double jacc;
@@ -142,6 +145,7 @@ template <class F, int NI_> struct Sh23Fwd {
     cplx* C = reinterpret_cast<cplx*>(smem) + (size_t)li * PER_INST;
     cplx* XA = C + Cr::NHMAX;
     cplx* XB = XA + Cr::XLEN;
+    double* IA = reinterpret_cast<double*>(XB + Cr::XLEN);
     const int Nh = p.Nh, NIT = p.n_iters;
     const bool prep = (p.flags & 2) != 0;
     const int n = step - 1;
@@ -149,7 +153,10 @@ template <class F, int NI_> struct Sh23Fwd {
     const bool do_inv = (step >= 1) && !fin;
     const bool do_upd = do_inv && (n < NIT || prep);
     if (PH == 0) {
-      if (step == 0) st.jacc = 0.0;
+      if (step == 0) {
+        st.jacc = 0.0;
+        for (int k = jj; k < Nh; k += RT) IA[k] = 1.0 / sh_A(p, k);
+      }
       if (do_inv) {
         if (live && !prep) {
           cplx* dst = p.snaps + ((long long)inst * (NIT + 1) + n) * Nh;
@@ -215,8 +222,8 @@ template <class F, int NI_> struct Sh23Fwd {
         for (int k = jj; k < Nh; k += RT) {
           const cplx nh = Cr::postprocess(p, XA, k);
           const cplx c = C[k];
-          const double A = sh_A(p, k);
-          C[k] = make_double2((c.x / p.dt + nh.x) / A, (c.y / p.dt + nh.y) / A);
+          const double iA = IA[k];
+          C[k] = make_double2((c.x * p.inv_dt + nh.x) * iA, (c.y * p.inv_dt + nh.y) * iA);
         }
       }
     }
@@ -231,8 +238,9 @@ template <class F, int NI_> struct Sh23Adj {
   static constexpr int THREADS = NI_ * RT;
   static constexpr int NPHASES = 4;
   static constexpr int MIN_BLOCKS = 1;
-  static constexpr int PER_INST = 2 * Cr::NHMAX + 3 * Cr::XLEN;   // C (= q) | S (snapshot) | XA | XB | XC
+  static constexpr int PER_INST = 2 * Cr::NHMAX + 3 * Cr::XLEN + Cr::NHMAX / 2;   // C (= q) | S (snapshot) | XA | XB | XC | 1/A_k
   static constexpr size_t SMEM = (size_t)NI_ * PER_INST * sizeof(cplx);
+  SMO_HD static constexpr int sync_after(int) { return (32 % RT == 0) ? 1 : 2; }
   struct State {
     double re[RT], im[RT];
     double ur[RT], ui[RT];
@@ -247,6 +255,7 @@ template <class F, int NI_> struct Sh23Adj {
     cplx* XA = S + Cr::NHMAX;
     cplx* XB = XA + Cr::XLEN;
     cplx* XC = XB + Cr::XLEN;
+    double* IA = reinterpret_cast<double*>(XC + Cr::XLEN);
     const int Nh = p.Nh, NIT = p.n_iters;
     const bool cont = (p.flags & 1) != 0;
     const bool fin = (step == NIT + 1);
@@ -290,15 +299,17 @@ template <class F, int NI_> struct Sh23Adj {
         // terminal condition: discrete q0 = -2 u^N/(1/dt + L) (FWD_Solve_SH23.py:584), continuous q0 = 0
         for (int k = jj; k < Nh; k += RT) {
           cplx q = make_double2(0.0, 0.0);
-          if (!cont && live) { const cplx f = snaps[(long long)NIT * Nh + k]; const double A = sh_A(p, k); q = make_double2(-2.0 * f.x / A, -2.0 * f.y / A); }
+          const double iA = 1.0 / sh_A(p, k);
+          IA[k] = iA;
+          if (!cont && live) { const cplx f = snaps[(long long)NIT * Nh + k]; q = make_double2(-2.0 * f.x * iA, -2.0 * f.y * iA); }
           C[k] = q;
         }
       } else if (do_step) {
         for (int k = jj; k < Nh; k += RT) {
           const cplx rh = Cr::postprocess(p, XA, k);
           const cplx c = C[k];
-          const double A = sh_A(p, k);
-          C[k] = make_double2((c.x / p.dt + rh.x) / A, (c.y / p.dt + rh.y) / A);
+          const double iA = IA[k];
+          C[k] = make_double2((c.x * p.inv_dt + rh.x) * iA, (c.y * p.inv_dt + rh.y) * iA);
         }
       }
       // prefetch the forward snapshot of the NEXT adjoint step m = step: index -2-m (discrete), -1-m (continuous)

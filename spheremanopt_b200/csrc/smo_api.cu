@@ -272,7 +272,7 @@ template <int H> static int sh23_run(smo_sh23* h, bool adj, Sh23Params& p, rt_st
 }
 static int sh23_dispatch(smo_sh23* h, bool adj, Sh23Params& p, rt_stream st) {
   p.nwork = (p.batch + SH_NI - 1) / SH_NI;
-  p.Nh = h->Nh; p.a = h->a; p.kfac = 2.0 * 3.14159265358979323846 / h->L;
+  p.Nh = h->Nh; p.a = h->a; p.kfac = 2.0 * 3.14159265358979323846 / h->L; p.inv_dt = 1.0 / p.dt;
   p.twH = h->twH; p.twM = h->twM;
   switch (h->H) {
     case 64: return sh23_run<64>(h, adj, p, st);

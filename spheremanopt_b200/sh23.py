@@ -156,7 +156,9 @@ def ADJ_Solve_IVP_Lin(X_k, domain, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, filenam
     G = adjoint_batch(domain, dt, N_ITERS, X_FWD_DICT, Adjoint_type)
     if isinstance(X_k[0], DevVec):
         return [DevVec(G)]
-    return [G.cpu().numpy()]
+    out = torch.empty(G.numel(), dtype=G.dtype, pin_memory=True)    # page-locked D2H (see kdyn.Domain.host_from_slab)
+    out.copy_(G)
+    return [out.numpy()]
 
 
 def FWD_Solve_IVP_PREP(X_k, domain, dt=1e-02, N_ITERS=100, N_SUB_ITERS=100):
