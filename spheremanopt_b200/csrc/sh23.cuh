@@ -236,9 +236,10 @@ template <class F, int NI_> struct Sh23Adj {
   typedef Sh23Core<F> Cr;
   static constexpr int NI = NI_, RT = F::RT, R1 = F::R1, R2 = F::R2, M = Cr::M;
   static constexpr int THREADS = NI_ * RT;
-  static constexpr int NPHASES = 4;
+  static constexpr int NPHASES = 5;
   static constexpr int MIN_BLOCKS = 1;
-  static constexpr int PER_INST = 2 * Cr::NHMAX + 3 * Cr::XLEN + Cr::NHMAX / 2;   // C (= q) | S (snapshot) | XA | XB | XC | 1/A_k
+  // C (= q) | S (snapshot) | XA | XB | 1/A_k ; the forward exchange re-uses XB one (warp) barrier after the inverse read it
+  static constexpr int PER_INST = 2 * Cr::NHMAX + 2 * Cr::XLEN + Cr::NHMAX / 2;
   static constexpr size_t SMEM = (size_t)NI_ * PER_INST * sizeof(cplx);
   SMO_HD static constexpr int sync_after(int) { return (32 % RT == 0) ? 1 : 2; }
   struct State {
@@ -254,8 +255,8 @@ template <class F, int NI_> struct Sh23Adj {
     cplx* S = C + Cr::NHMAX;
     cplx* XA = S + Cr::NHMAX;
     cplx* XB = XA + Cr::XLEN;
-    cplx* XC = XB + Cr::XLEN;
-    double* IA = reinterpret_cast<double*>(XC + Cr::XLEN);
+    cplx* XC = XB;
+    double* IA = reinterpret_cast<double*>(XB + Cr::XLEN);
     const int Nh = p.Nh, NIT = p.n_iters;
     const bool cont = (p.flags & 1) != 0;
     const bool fin = (step == NIT + 1);
@@ -279,7 +280,6 @@ template <class F, int NI_> struct Sh23Adj {
             st.im[i] = (3.6 * u1 - 3.0 * (u1 * u1)) * st.im[i] - 2.0 * u1;
           }
         }
-        Cr::fwd_stage1(p, jj, XC, st.re, st.im);
       }
       if (fin) {
         Cr::inv_stage2(XA, jj, st.re, st.im);
@@ -293,6 +293,8 @@ template <class F, int NI_> struct Sh23Adj {
         }
       }
     } else if (PH == 2) {
+      if (do_step) Cr::fwd_stage1(p, jj, XC, st.re, st.im);
+    } else if (PH == 3) {
       if (do_step) Cr::fwd_stage2(XC, XA, jj, st.re, st.im);
     } else {
       if (step == 0) {
