@@ -60,6 +60,14 @@ SMO_HD void cp_async16(void* sdst, const void* gsrc) {
   memcpy(sdst, gsrc, 16);
 #endif
 }
+// fire-and-forget prefetch of the 128-byte line holding p into L2 (hides the HBM latency of a later plain load)
+SMO_HD void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 SMO_HD void cp_async_commit() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;" ::: "memory");

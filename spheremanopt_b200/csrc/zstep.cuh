@@ -22,7 +22,7 @@
 #include "kd_epilogue.cuh"
 
 #ifndef SMO_ZS_MB
-#define SMO_ZS_MB 5     // resident CTAs per SM the register allocation of the fused z step is bounded for
+#define SMO_ZS_MB 4     // resident CTAs per SM the register allocation of the fused z step is bounded for (55 KB of smem each)
 #endif
 
 namespace smo {
@@ -61,8 +61,8 @@ template <class F, int T_> struct ZStep {
   static constexpr int NPHASES = 9;
   static constexpr int MIN_BLOCKS = (F::RT > 16) ? 2 : SMO_ZS_MB;
   static constexpr bool WARP_OK = (32 % F::RT == 0);       // the RT threads of a line never straddle a warp
-  static constexpr int LAND = 3 * T_ * M, WORK = 3 * T_ * XP;
-  static constexpr size_t SMEM = (size_t)(LAND + WORK + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int);
+  static constexpr int LAND = 3 * T_ * M, WORK = 3 * T_ * XP, STATE = 3 * T_ * PC;
+  static constexpr size_t SMEM = (size_t)(LAND + WORK + STATE + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int);
   static_assert(XP >= PC, "compact coefficient line must fit into the exchange line");
   struct State {
     double re[F::RT], im[F::RT];
@@ -73,7 +73,8 @@ template <class F, int T_> struct ZStep {
 
   SMO_HD static cplx* land(unsigned char* s) { return reinterpret_cast<cplx*>(s); }
   SMO_HD static cplx* wrk(unsigned char* s) { return land(s) + LAND; }
-  SMO_HD static cplx* twid(unsigned char* s) { return wrk(s) + WORK; }
+  SMO_HD static cplx* stl(unsigned char* s) { return wrk(s) + WORK; }      // coefficient state of the tile (cp.async target)
+  SMO_HD static cplx* twid(unsigned char* s) { return stl(s) + STATE; }
   SMO_HD static int* segidx(unsigned char* s) { return reinterpret_cast<int*>(twid(s) + M); }   // n / seglen
   SMO_HD static int* segrem(unsigned char* s) { return segidx(s) + M; }                         // n % seglen
 
@@ -109,6 +110,34 @@ template <class F, int T_> struct ZStep {
     }
   }
 
+  // the thread's own line of the coefficient state (B^n | G | nu) -> shared memory, asynchronously; issued once the
+  // pointwise update of the previous tile has consumed the buffer
+  SMO_HD static void load_state(const Params& p, int work, const Ctx& c) {
+    int f, t, jj, tile, trip;
+    split_tid(c.tid, f, t, jj);
+    decode(p, work, tile, trip);
+    const int b = tile * T + t;
+    if (b >= p.nlines) return;
+    cplx* Sd = stl(c.smem) + (f * T + t) * PC;
+    const cplx* src = p.b[3 * trip + f] + (long long)b * p.Pc;
+    for (int e = jj; e < PC; e += RT) cp_async16(&Sd[e], src + e);
+  }
+  // L2 prefetch of the coefficient-state lines (and the next forward snapshot) the pointwise update of `work` will read
+  // with plain loads: 2 KB per line and field = 16 lines of 128 bytes
+  SMO_HD static void prefetch_state(const Params& p, int work, const Ctx& c) {
+    int tile, trip;
+    decode(p, work, tile, trip);
+    const int per_line = (PC * (int)sizeof(cplx)) / 128;
+    const int kind = (p.mode == 0) ? 0 : 1 + trip;
+    if (!(kind == 2 && p.do_inv)) return;    // only the next forward snapshot is still read with plain loads
+    for (int q = c.tid; q < 3 * T * per_line; q += THREADS) {
+      const int arr = q / (T * per_line), r = q % (T * per_line);
+      const int bl = tile * T + r / per_line;
+      if (bl >= p.nlines) continue;
+      prefetch_l2(p.nxt[arr] + (long long)bl * p.Pc + (r % per_line) * (128 / (int)sizeof(cplx)));
+    }
+  }
+
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
     cplx* W = twid(c.smem);
     for (int m = c.tid; m < M; m += THREADS) W[m] = ldg_c(p.tw + ((m % R2) * (m / R2)) % M);
@@ -131,7 +160,7 @@ template <class F, int T_> struct ZStep {
     cplx* Ld = land(c.smem) + (f * T + t) * M;
     cplx* Wk = wrk(c.smem) + (f * T + t) * XP;
     if (PH == 0) {
-      if (st.it == 0) load_tile(p, work, c);
+      if (st.it == 0) { load_tile(p, work, c); load_state(p, work, c); prefetch_state(p, work, c); }
       cp_async_commit();
       cp_async_wait<0>();
     } else if (PH == 1) {
@@ -154,7 +183,7 @@ template <class F, int T_> struct ZStep {
       }
     } else if (PH == 2) {
       // the landing line is consumed: stream in the same line of this CTA's next work item
-      if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, c);
+      if (work + c.ncta < p.nwork) { load_tile(p, work + c.ncta, c); prefetch_state(p, work + c.ncta, c); }
       cp_async_commit();
       if (jj < R2 && live) {
 #pragma unroll
@@ -203,7 +232,8 @@ template <class F, int T_> struct ZStep {
         const int sb = 3 * trip;
         if (kind == 2 && p.do_inv) nw = load3(p.nxt, 0, idx);
         if (!k0) {
-          const C3 S = load3(p.b, sb, idx);
+          const cplx* Ss = stl(c.smem) + tt * PC + iz;
+          C3 S; S.x = Ss[0]; S.y = Ss[T * PC]; S.z = Ss[2 * T * PC];
           if (kind == 0) {
             const double alpha = 1.0 / p.dt + w.k2 / (2.0 * p.Rm), beta = 1.0 / p.dt - w.k2 / (2.0 * p.Rm);
             so = proj_scale_minus(w, axpy3(beta, S, curl3(w, A)), 1.0 / alpha, kdot_over_k2(w, S));
@@ -220,6 +250,9 @@ template <class F, int T_> struct ZStep {
         *w0 = nw.x; *w1 = nw.y; *w2 = nw.z;
       }
     } else if (PH == 6) {
+      // the state buffer is consumed (CTA barrier after phase 5): stream in the state of this CTA's next work item
+      if (work + c.ncta < p.nwork) load_state(p, work + c.ncta, c);
+      cp_async_commit();
       // inverse stage 1 on the zero-padded compact line
       if (p.do_inv && jj < R2 && live) {
 #pragma unroll
