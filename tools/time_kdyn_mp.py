@@ -36,6 +36,9 @@ names = {0: "total", 1: "z-pass", 2: "y-pass", 3: "x-fwd", 5: "a2a", 6: "x-adj",
 for k, v in os.environ.items():
     if k.startswith("SMO_OPT_"):
         lib.smo_kdyn_set_option(dom.h, int(k[8:]), int(v))
+if os.environ.get("CHUNKS"):
+    cf, ca = (int(v) for v in os.environ["CHUNKS"].split(","))
+    lib.smo_kdyn_set_chunks(dom.h, cf, ca)
 if os.environ.get("GRAPH"):
     lib.smo_kdyn_use_graph(dom.h, 1)
 for _ in range(3):
