@@ -84,7 +84,7 @@ SMO_HD C3 axpy3(double s, const C3& x, const C3& y) {   // s*x + y
   return o;
 }
 
-enum { EPI_FWD = 0, EPI_ADJ = 1, EPI_COMPAT = 2, EPI_FINAL = 3, EPI_CURL = 4 };
+enum { EPI_FWD = 0, EPI_ADJ = 1, EPI_COMPAT = 2, EPI_FINAL = 3, EPI_CURL = 4, EPI_NUFIN = 5 };
 
 // EPI_FWD   : a[0..2] = to_coef(U x B) (EMF), b[0..2] = B^n            -> o[0..2] = B^{n+1}
 // EPI_ADJ   : a[0..2] = to_coef(W x U), a[3..5] = to_coef(W x B_f), b[0..2] = G, b[3..5] = nu
@@ -92,6 +92,9 @@ enum { EPI_FWD = 0, EPI_ADJ = 1, EPI_COMPAT = 2, EPI_FINAL = 3, EPI_CURL = 4 };
 // EPI_COMPAT: b[0..2] = B^N -> o[0..2] = G^0, o2[0..2] = i k x G^0   (flag&1 Integrated, flag&2 Continuous)
 // EPI_FINAL : b[0..2] = G^N -> o[0..2] = dt*alpha*G^N  (flag&2 Continuous: plain copy)
 // EPI_CURL  : b[0..2] = G   -> o2[0..2] = i k x G        (segment boundaries of a checkpointed adjoint sweep)
+// EPI_NUFIN : b[0..2] = to_coef(sum_m (curl G^m) x B_f^m) -> o[0..2] = nu^N = -dt P_k[b]   (KD:874-877 summed over the sweep:
+//             nu' = nu + dt P_k[-H] with nu^0 = 0 is linear in H, so the sum is taken before the transforms, see xpass.cuh)
+// EPI_ADJ flag&4: the nu update is left out (a[3..5], b[3..5], o[3..5] unused)
 template <int KIND> struct EpiKernel {
   typedef EpiParams Params;
   static constexpr int THREADS = 256;
@@ -121,17 +124,19 @@ template <int KIND> struct EpiKernel {
       C3 Gn = zero3(), Nn = zero3(), Wn = zero3();
       if (!k0) {
         const C3 G = load3(p.b, 0, idx);
-        const C3 Nu = load3(p.b, 3, idx);
         C3 HG = load3(p.a, 0, idx);
         if (p.flag & 1) HG = axpy3(-2.0, load3(p.o2, 3, idx), HG);
-        const C3 HN = load3(p.a, 3, idx);
         Gn = proj_scale_minus(w, axpy3(beta, G, HG), 1.0 / alpha, kdot_over_k2(w, G));
-        // nu-system: alpha = beta = 1/dt, F = -HN  =>  nu' = P[nu - dt*HN] - k (k.nu)/k^2
-        Nn = proj_scale_minus(w, axpy3(-p.dt, HN, Nu), 1.0, kdot_over_k2(w, Nu));
+        if (!(p.flag & 4)) {
+          // nu-system: alpha = beta = 1/dt, F = -HN  =>  nu' = P[nu - dt*HN] - k (k.nu)/k^2
+          const C3 Nu = load3(p.b, 3, idx);
+          const C3 HN = load3(p.a, 3, idx);
+          Nn = proj_scale_minus(w, axpy3(-p.dt, HN, Nu), 1.0, kdot_over_k2(w, Nu));
+        }
         Wn = curl3(w, Gn);
       }
       store3(p.o, 0, idx, Gn);
-      store3(p.o, 3, idx, Nn);
+      if (!(p.flag & 4)) store3(p.o, 3, idx, Nn);
       store3(p.o2, 0, idx, Wn);
     } else if (KIND == EPI_COMPAT) {
       C3 G = zero3(), Wn = zero3();
@@ -146,6 +151,8 @@ template <int KIND> struct EpiKernel {
       }
       store3(p.o, 0, idx, G);
       store3(p.o2, 0, idx, Wn);
+    } else if (KIND == EPI_NUFIN) {
+      store3(p.o, 0, idx, k0 ? zero3() : proj_scale_minus(w, load3(p.b, 0, idx), -p.dt, cmk(0.0, 0.0)));
     } else if (KIND == EPI_CURL) {
       store3(p.o2, 0, idx, k0 ? zero3() : curl3(w, load3(p.b, 0, idx)));
     } else {

@@ -424,6 +424,7 @@ struct smo_kdyn {
   cplx* p2[MAXF];    // [Nh][M][nz]
   cplx* cw[MAXF];    // coefficient work
   cplx* G[3]; cplx* NU[3]; cplx* W[3];
+  cplx* acc[3];      // [Nh][M][nz] running sum over the adjoint steps of the x-spectra of (curl G) x B_f (allocated on first use)
   double* Ug[3];     // projected velocity on the grid [M][M][nz]
   double* Ut;        // the same, tile-major [M*nz/4][3][M][4] (read by the fused x passes)
   double* gwork;     // 3*gsize doubles
@@ -738,6 +739,8 @@ template <int M> struct KdOps {
   static int x_adj(smo_kdyn* h, cplx* const* io, rt_stream st, int z0 = 0, int nzc = -1) {
     XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 6; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
+    for (int c = 0; c < 3; ++c) p.sout[3 + c] = h->acc[c];    // (curl G) x B_f: summed over the sweep on the x-spectra
+    p.accumulate = 1;
     prof_begin(h, PK_XA, st);
     int rc = launch<XFused<F, X_ADJ>>(p, st);
     prof_end(h, PK_XA, st);
@@ -780,12 +783,10 @@ template <int M> struct KdOps {
     if (mode == 0) {
       for (int c = 0; c < 3; ++c) { p.b[c] = Bn[c]; p.o[c] = Bnp1[c]; }
     } else {
-      for (int c = 0; c < 3; ++c) {
-        p.b[c] = h->G[c]; p.o[c] = h->G[c]; p.b[3 + c] = h->NU[c]; p.o[3 + c] = h->NU[c];
-        p.nxt[c] = nxt ? nxt[c] : nullptr;
-      }
+      // triplet 0: G update from (curl G) x U, next operand curl G'; triplet 1: the next forward snapshot, inverse only
+      for (int c = 0; c < 3; ++c) { p.b[c] = h->G[c]; p.o[c] = h->G[c]; p.b[3 + c] = nxt ? nxt[c] : nullptr; }
     }
-    p.nsteps = 1; p.mode = mode; p.ntrip = mode == 0 ? 1 : 2;
+    p.nsteps = 1; p.mode = mode; p.ntrip = (mode == 1 && do_inv) ? 2 : 1;
     p.nlines = h->nkx * h->Nc; p.tiles = (p.nlines + TZS - 1) / TZS; p.nwork = p.tiles * p.ntrip;
     p.do_inv = do_inv ? 1 : 0;
     p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
@@ -814,7 +815,7 @@ template <int M> struct KdOps {
       TRY(inv_y(h, h->p1t, h->p2, nf, st, z0, nch > 1 ? nzc : -1, ch == 0 ? XS_B : XS_NONE));
       if (nf == 3) TRY(x_fwd(h, h->p2, st, z0, nch > 1 ? nzc : -1));
       else TRY(x_adj(h, h->p2, st, z0, nch > 1 ? nzc : -1));
-      TRY(fwd_y(h, h->p2, h->p1t, nf, st, z0, nch > 1 ? nzc : -1, ch == nch - 1 ? XS_A : XS_NONE));
+      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, nch > 1 ? nzc : -1, ch == nch - 1 ? XS_A : XS_NONE));
     }
     return 0;
   }
@@ -856,15 +857,15 @@ template <int M> struct KdOps {
       const int z0 = ch * nzc;
       TRY(inv_y(h, h->p1t, h->p2, 6, st, z0, nch > 1 ? nzc : -1));
       TRY(x_adj(h, h->p2, st, z0, nch > 1 ? nzc : -1));
-      TRY(fwd_y(h, h->p2, h->p1t, 6, st, z0, nch > 1 ? nzc : -1));
+      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, nch > 1 ? nzc : -1));
     }
-    TRY(a2a(h, h->p1t, h->p1, 6, st));
-    TRY(fwd_z(h, h->p1, h->cw, 6, st));
-    EpiParams e; efill(e, h, Rm, dt, flag);
-    for (int c = 0; c < 6; ++c) e.a[c] = h->cw[c];
+    TRY(a2a(h, h->p1t, h->p1, 3, st));
+    TRY(fwd_z(h, h->p1, h->cw, 3, st));
+    EpiParams e; efill(e, h, Rm, dt, flag | 4);     // nu is accumulated by the x pass (flag 4: no nu update here)
+    for (int c = 0; c < 3; ++c) e.a[c] = h->cw[c];
     for (int c = 0; c < 3; ++c) {
-      e.b[c] = h->G[c]; e.b[3 + c] = h->NU[c];
-      e.o[c] = h->G[c]; e.o[3 + c] = h->NU[c];
+      e.b[c] = h->G[c];
+      e.o[c] = h->G[c];
       e.o2[c] = h->W[c]; e.o2[3 + c] = const_cast<cplx*>(Bf[c]);
     }
     prof_begin(h, PK_EPI, st);
@@ -881,6 +882,24 @@ template <int M> struct KdOps {
     EpiParams e; efill(e, h, Rm, dt, 0);
     for (int c = 0; c < 3; ++c) { e.b[c] = h->G[c]; e.o2[c] = h->W[c]; }
     return launch<EpiKernel<EPI_CURL>>(e, st);
+  }
+  // start of an adjoint sweep: the running sum of the (curl G) x B_f spectra is cleared
+  static int acc_begin(smo_kdyn* h, rt_stream st) {
+    for (int c = 0; c < 3; ++c) {
+      if (!h->acc[c]) TRY(rt_malloc((void**)&h->acc[c], sizeof(cplx) * h->p2size));
+      TRY(rt_memset(h->acc[c], 0, sizeof(cplx) * h->p2size, st));
+    }
+    return 0;
+  }
+  // end of the sweep: nu^N = -dt P_k[ y/z transforms of the running sum ]   (once instead of every step)
+  static int nu_finish(smo_kdyn* h, double Rm, double dt, rt_stream st) {
+    if (h->peer_on) TRY(a2a(h, h->p1t, h->p1, 3, st));
+    TRY(fwd_y(h, h->acc, h->p1t, 3, st));
+    TRY(a2a(h, h->p1t, h->p1, 3, st));
+    TRY(fwd_z(h, h->p1, h->cw, 3, st));
+    EpiParams e; efill(e, h, Rm, dt, 0);
+    for (int c = 0; c < 3; ++c) { e.b[c] = h->cw[c]; e.o[c] = h->NU[c]; }
+    return launch<EpiKernel<EPI_NUFIN>>(e, st);
   }
   static int final_scale(smo_kdyn* h, double Rm, double dt, int flag, rt_stream st) {
     EpiParams e; efill(e, h, Rm, dt, flag);
@@ -1054,6 +1073,7 @@ static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn
   });
 }
 template <int M> static int kd_adjoint_finish(smo_kdyn* h, double Rm, double dt, int cont, double* gB, double* gU, rt_stream st) {
+  TRY(KdOps<M>::nu_finish(h, Rm, dt, st));
   TRY(KdOps<M>::final_scale(h, Rm, dt, cont, st));
   TRY(KdOps<M>::to_grid(h, h->cw, gB, st));
   TRY(KdOps<M>::to_grid(h, h->NU, gU, st));
@@ -1066,7 +1086,7 @@ template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_
   cplx* s[3];
   snap_ptrs(h, const_cast<void*>(snaps), n_iters, s);
   TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
-  for (int c = 0; c < 3; ++c) TRY(rt_memset(h->NU[c], 0, sizeof(cplx) * h->csize, st));
+  TRY(KdOps<M>::acc_begin(h, st));
   // adjoint step m linearises about snapshot idx(m): snapshot_index -1-m (continuous) / -2-m (discrete)
   SnapState sn; sn.h = h; sn.snaps = const_cast<void*>(snaps); sn.flip = 0;
   auto state = [&](int m) { return sn(cont ? (n_iters - m) : (n_iters - 1 - m)); };
@@ -1109,7 +1129,7 @@ template <int M> static int kd_adjoint_ckpt(smo_kdyn* h, double Rm, double dt, i
   cplx* s[3];
   snap_ptrs(h, ck, ckpt_slot_of(n_iters, n_iters, every), s);
   TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
-  for (int c = 0; c < 3; ++c) TRY(rt_memset(h->NU[c], 0, sizeof(cplx) * h->csize, st));
+  TRY(KdOps<M>::acc_begin(h, st));
   const int nseg = (n_iters + every - 1) / every;
   for (int k = nseg - 1; k >= 0; --k) {
     const int n0 = k * every, n1 = (n0 + every < n_iters) ? n0 + every : n_iters;   // the segment holds the states n0 .. n1
@@ -1175,7 +1195,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->hB = h->hU = h->hGB = h->hGU = nullptr; h->snaps = nullptr; h->cap_snap = 0;
   h->tw = nullptr; h->gwork = nullptr; h->vwork = nullptr;
   for (int f = 0; f < MAXF; ++f) h->p1[f] = h->p1t[f] = h->p2[f] = h->cw[f] = nullptr;
-  for (int c = 0; c < 3; ++c) { h->G[c] = h->NU[c] = h->W[c] = nullptr; h->Ug[c] = nullptr; }
+  for (int c = 0; c < 3; ++c) { h->G[c] = h->NU[c] = h->W[c] = nullptr; h->Ug[c] = nullptr; h->acc[c] = nullptr; }
   h->Ut = nullptr;
 #if !defined(SMO_EMUL)
   h->ev = new std::vector<cudaEvent_t>(); h->ev_used = 0;
@@ -1211,7 +1231,7 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
     if (h->nranks > 1) rt_free(h->p1t[f]);
     rt_free(h->p1[f]); rt_free(h->p2[f]); rt_free(h->cw[f]);
   }
-  for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); }
+  for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); rt_free(h->acc[c]); }
   rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut);
 #if !defined(SMO_EMUL)
   if (h->peer_on) {

@@ -229,6 +229,7 @@ struct XFParams {
   int tiles_per_row, row_tiles, tile0;   // column tile of work w: (w / tiles_per_row) * row_tiles + tile0 + w % tiles_per_row
   double scale;
   const cplx* tw;
+  int accumulate;            // X_ADJ: outputs 3..5 (x-spectra of (curl G) x B_f) are ADDED to sout[3..5] instead of stored
 };
 
 template <class F, int MODE> struct XFused {
@@ -255,7 +256,12 @@ template <class F, int MODE> struct XFused {
   static constexpr int SIN_ELEMS = NF * NH * T;      // cplx (16-byte units)
   static constexpr int SU_UNITS = 3 * M * 2;         // 16-byte units of the 4-column velocity block
   static constexpr int X_ELEMS = NJ * XLP;
-  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS) * sizeof(cplx);
+  // Adjoint: the gradient integrand  nu = -dt * sum_m P_k[ F((curl G^m) x B_f^m) ]  is linear in the products, so the sum
+  // over the time steps is taken on the x-spectra (this kernel adds its (curl G) x B_f outputs to a running array) and
+  // the y / z transforms, the transpose and the projection are applied ONCE after the sweep instead of every step.
+  // The running array's tile is streamed in with cp.async while the tile is transformed.
+  static constexpr int ACC_ELEMS = (MODE == X_ADJ) ? 3 * NH * T : 0;
+  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS + ACC_ELEMS) * sizeof(cplx);
   static_assert(R1 >= R2 && RT == R1, "the radix-R1 stage is the wide one");
   static_assert(SIN_ELEMS % 8 == 0 && SU_UNITS % 8 == 0, "cp.async regions must be whole 128-byte lines");
   static_assert(MODE == X_FWD || MODE == X_ADJ, "fused modes only");
@@ -269,6 +275,7 @@ template <class F, int MODE> struct XFused {
   SMO_HD static cplx* sin_buf(unsigned char* s) { return reinterpret_cast<cplx*>(s); }
   SMO_HD static cplx* su_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
   SMO_HD static cplx* x_buf(unsigned char* s) { return su_buf(s) + SU_UNITS; }
+  SMO_HD static cplx* acc_buf(unsigned char* s) { return x_buf(s) + X_ELEMS; }
   // unit index of spectral entry (field f, row, tile column col): two rows per 128-byte line
   SMO_HD static int si(int f, int row, int col) {
     return (((f * NH + row) >> 1) << 3) + ((((row & 1) << 2) + col) ^ ((row >> 1) & 3));
@@ -291,6 +298,18 @@ template <class F, int MODE> struct XFused {
     for (int q = c.tid % FT; q < NH * T; q += FT) {
       const int tc = q % T, row = q / T;
       cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+    }
+  }
+  // running-sum tile of the field this warp produces (fields 3..5 only), consumed by phase 8 of the same work item
+  SMO_HD static void load_acc(const Params& p, int work, const Ctx& c) {
+    const int f = c.tid / FT;
+    if (MODE != X_ADJ || f < 3) return;
+    cplx* A = acc_buf(c.smem);
+    const long long col0 = tile_of(p, work) * T;
+    const cplx* src = p.sout[out_field(f)];
+    for (int q = c.tid % FT; q < NH * T; q += FT) {
+      const int tc = q % T, row = q / T;
+      cp_async16(&A[si(f - 3, row, tc)], src + (long long)row * p.ncols + col0 + tc);
     }
   }
   SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
@@ -351,6 +370,7 @@ template <class F, int MODE> struct XFused {
     }
     if (PH == 2) {
       if (more) load_sin(p, work + c.ncta, c);   // the spectral buffer was consumed in phase 1
+      if (MODE == X_ADJ && p.accumulate) load_acc(p, work, c);
       cp_async_commit();
 #pragma unroll
       for (int j = 0; j < R2; ++j) {
@@ -423,6 +443,7 @@ template <class F, int MODE> struct XFused {
           if (k < NH || k > M - NH) Xn[k] = make_double2(st.re[k2], st.im[k2]);
         }
       }
+      if (MODE == X_ADJ) cp_async_wait<1>();     // the running-sum tile (committed in phase 2) has landed
     }
     if (PH == 8) {
       // own thread order (column pairs fastest) so that a row's T columns are stored by adjacent lanes
@@ -430,11 +451,19 @@ template <class F, int MODE> struct XFused {
       const cplx* X8 = x_buf(c.smem) + (f * HP + pp8) * XLP;
       cplx* O = p.sout[out_field(f)] + tile_of(p, work) * T + 2 * pp8;
       const double h = 0.5 * p.scale;
+      const bool addto = (MODE == X_ADJ) && p.accumulate && f >= 3;
+      const cplx* A = acc_buf(c.smem);
       for (int k = kk; k < NH; k += RT) {
         const cplx zk = X8[k];
         const cplx zm = X8[(M - k) % M];
-        O[(long long)k * p.ncols] = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
-        O[(long long)k * p.ncols + 1] = make_double2(h * (zk.y + zm.y), h * (zm.x - zk.x));
+        cplx o0 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));
+        cplx o1 = make_double2(h * (zk.y + zm.y), h * (zm.x - zk.x));
+        if (addto) {
+          const cplx a0 = A[si(f - 3, k, 2 * pp8)], a1 = A[si(f - 3, k, 2 * pp8 + 1)];
+          o0.x += a0.x; o0.y += a0.y; o1.x += a1.x; o1.y += a1.y;
+        }
+        O[(long long)k * p.ncols] = o0;
+        O[(long long)k * p.ncols + 1] = o1;
       }
       st.it++;
     }

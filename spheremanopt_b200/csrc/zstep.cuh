@@ -11,7 +11,8 @@
 // A work item is a *triplet*: the three vector components of T adjacent z lines (a z line = all kz of one (kx, ky)).
 //   forward step : 1 triplet per tile  - in = to_p1(U x B^n),        state B^n -> B^{n+1},   next operand B^{n+1}
 //   adjoint step : 2 triplets per tile - in = to_p1((curl G) x U),   state G -> G',          next operand curl G'
-//                                        in = to_p1((curl G) x B_f), state nu -> nu',        next operand B_f (next snapshot)
+//                                        no input, no update:                               next operand B_f (next snapshot)
+//   (the gradient integrand nu is accumulated on the x-spectra by the x pass and transformed once after the sweep)
 // Thread (f, t, jj): component f, line t, stage thread jj < RT.  With RT dividing 32 all exchanges of a line stay
 // inside one warp, so only the two barriers around the pointwise update (which mixes the three components) are
 // CTA-wide; everything else is a __syncwarp (smo_common.cuh: sync_after).
@@ -30,11 +31,11 @@ namespace smo {
 struct ZParams {
   const cplx* in[MAXF];     // p1 inputs (kx-slab side), one per field
   cplx* out[MAXF];          // p1 outputs (local buffer; peer buffers below when peer_mode != 0)
-  const cplx* b[MAXF];      // coefficient state in  : forward B^n[3]    | adjoint G[3], nu[3]
-  cplx* o[MAXF];            // coefficient state out : forward B^{n+1}[3] | adjoint G'[3], nu'[3]
-  const cplx* nxt[3];       // adjoint: forward-state snapshot the next adjoint step linearises about
+  const cplx* b[MAXF];      // coefficient state in  : forward B^n[3]    | adjoint G[3], then the forward-state snapshot
+                            //                         the next adjoint step linearises about [3]
+  cplx* o[MAXF];            // coefficient state out : forward B^{n+1}[3] | adjoint G'[3]
   int nwork, nsteps;        // nwork = tiles * ntrip
-  int ntrip, mode;          // mode 0: forward CNAB1 step (ntrip 1); mode 1: adjoint step (ntrip 2)
+  int ntrip, mode;          // mode 0: forward CNAB1 step (ntrip 1); mode 1: adjoint step (ntrip 2, or 1 when nothing follows)
   int nlines, tiles;        // z lines of this rank = nkx*Nc
   int do_inv;               // 0: last step of a loop, nothing follows on the grid side
   int Nc, Pc, kmax, kx0;
@@ -93,7 +94,7 @@ template <class F, int T_> struct ZStep {
     split_tid(c.tid, f, t, jj);
     decode(p, work, tile, trip);
     const int b = tile * T + t;
-    if (b >= p.nlines) return;
+    if (b >= p.nlines || trip == 1) return;      // the second triplet of an adjoint step has no pencil input
     cplx* Ld = land(c.smem) + (f * T + t) * M;
     const cplx* src = p.in[3 * trip + f] + (long long)b * p.line_stride;
     if (p.seglen <= 0) {
@@ -122,22 +123,6 @@ template <class F, int T_> struct ZStep {
     const cplx* src = p.b[3 * trip + f] + (long long)b * p.Pc;
     for (int e = jj; e < PC; e += RT) cp_async16(&Sd[e], src + e);
   }
-  // L2 prefetch of the coefficient-state lines (and the next forward snapshot) the pointwise update of `work` will read
-  // with plain loads: 2 KB per line and field = 16 lines of 128 bytes
-  SMO_HD static void prefetch_state(const Params& p, int work, const Ctx& c) {
-    int tile, trip;
-    decode(p, work, tile, trip);
-    const int per_line = (PC * (int)sizeof(cplx)) / 128;
-    const int kind = (p.mode == 0) ? 0 : 1 + trip;
-    if (!(kind == 2 && p.do_inv)) return;    // only the next forward snapshot is still read with plain loads
-    for (int q = c.tid; q < 3 * T * per_line; q += THREADS) {
-      const int arr = q / (T * per_line), r = q % (T * per_line);
-      const int bl = tile * T + r / per_line;
-      if (bl >= p.nlines) continue;
-      prefetch_l2(p.nxt[arr] + (long long)bl * p.Pc + (r % per_line) * (128 / (int)sizeof(cplx)));
-    }
-  }
-
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
     cplx* W = twid(c.smem);
     for (int m = c.tid; m < M; m += THREADS) W[m] = ldg_c(p.tw + ((m % R2) * (m / R2)) % M);
@@ -157,15 +142,16 @@ template <class F, int T_> struct ZStep {
     decode(p, work, tile, trip);
     const int b = tile * T + t;
     const bool live = b < p.nlines;
+    const bool fwd = live && trip == 0;          // this triplet has a pencil input to transform and a state to update
     cplx* Ld = land(c.smem) + (f * T + t) * M;
     cplx* Wk = wrk(c.smem) + (f * T + t) * XP;
     if (PH == 0) {
-      if (st.it == 0) { load_tile(p, work, c); load_state(p, work, c); prefetch_state(p, work, c); }
+      if (st.it == 0) { load_tile(p, work, c); load_state(p, work, c); }
       cp_async_commit();
       cp_async_wait<0>();
     } else if (PH == 1) {
       // forward stage 1: thread j < R2 owns z samples j + R2*i
-      if (jj < R2 && live) {
+      if (jj < R2 && fwd) {
 #pragma unroll
         for (int i = 0; i < R1; ++i) {
           const cplx v = Ld[jj + R2 * i];
@@ -183,14 +169,14 @@ template <class F, int T_> struct ZStep {
       }
     } else if (PH == 2) {
       // the landing line is consumed: stream in the same line of this CTA's next work item
-      if (work + c.ncta < p.nwork) { load_tile(p, work + c.ncta, c); prefetch_state(p, work + c.ncta, c); }
+      if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, c);
       cp_async_commit();
-      if (jj < R2 && live) {
+      if (jj < R2 && fwd) {
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) Wk[jj * F::SK + k1] = make_double2(st.re[k1], st.im[k1]);
       }
     } else if (PH == 3) {
-      if (jj < R1 && live) {
+      if (jj < R1 && fwd) {
 #pragma unroll
         for (int j = 0; j < R2; ++j) {
           const cplx v = Wk[j * F::SK + jj];
@@ -200,7 +186,7 @@ template <class F, int T_> struct ZStep {
       }
     } else if (PH == 4) {
       // truncate: retained modes, scaled, in the compact order [0..kmax, -kmax..-1] (overwrites the exchange line)
-      if (jj < R1 && live) {
+      if (jj < R1 && fwd) {
 #pragma unroll
         for (int k2 = 0; k2 < R2; ++k2) {
           const int cidx = compact_index(jj + R1 * k2, M, KMAX);
@@ -209,12 +195,18 @@ template <class F, int T_> struct ZStep {
       }
     } else if (PH == 5) {
       // pointwise implicit update of the three components at (line, kz); consecutive threads -> consecutive kz
-      const int kind = (p.mode == 0) ? 0 : 1 + trip;
+      const int kind = (p.mode == 0) ? 0 : 1 + trip;      // 0 forward step, 1 adjoint G, 2 next forward snapshot (copy only)
       cplx* Wt = wrk(c.smem);
       for (int e = c.tid; e < T * PC; e += THREADS) {
         const int tt = e / PC, iz = e - tt * PC;
         const int bl = tile * T + tt;
         if (bl >= p.nlines || iz >= NC) continue;
+        cplx* w0 = Wt + (0 * T + tt) * XP + iz;
+        cplx* w1 = Wt + (1 * T + tt) * XP + iz;
+        cplx* w2 = Wt + (2 * T + tt) * XP + iz;
+        const cplx* Ss = stl(c.smem) + tt * PC + iz;
+        C3 S; S.x = Ss[0]; S.y = Ss[T * PC]; S.z = Ss[2 * T * PC];
+        if (kind == 2) { *w0 = S.x; *w1 = S.y; *w2 = S.z; continue; }
         const int ix = bl / p.Nc, iy = bl - ix * p.Nc;
         Wave w;
         w.kx = p.kfac * (double)(p.kx0 + ix);
@@ -222,31 +214,20 @@ template <class F, int T_> struct ZStep {
         w.kz = p.kfac * (double)(iz <= p.kmax ? iz : iz - p.Nc);
         w.k2 = w.kx * w.kx + w.ky * w.ky + w.kz * w.kz;
         w.valid = true;
-        const bool k0 = (w.k2 == 0.0);
         const long long idx = (long long)bl * p.Pc + iz;
-        cplx* w0 = Wt + (0 * T + tt) * XP + iz;
-        cplx* w1 = Wt + (1 * T + tt) * XP + iz;
-        cplx* w2 = Wt + (2 * T + tt) * XP + iz;
         C3 A; A.x = *w0; A.y = *w1; A.z = *w2;
         C3 nw = zero3(), so = zero3();    // next operand (-> inverse transform), new state (-> HBM)
-        const int sb = 3 * trip;
-        if (kind == 2 && p.do_inv) nw = load3(p.nxt, 0, idx);
-        if (!k0) {
-          const cplx* Ss = stl(c.smem) + tt * PC + iz;
-          C3 S; S.x = Ss[0]; S.y = Ss[T * PC]; S.z = Ss[2 * T * PC];
+        if (w.k2 != 0.0) {
+          const double alpha = 1.0 / p.dt + w.k2 / (2.0 * p.Rm), beta = 1.0 / p.dt - w.k2 / (2.0 * p.Rm);
           if (kind == 0) {
-            const double alpha = 1.0 / p.dt + w.k2 / (2.0 * p.Rm), beta = 1.0 / p.dt - w.k2 / (2.0 * p.Rm);
             so = proj_scale_minus(w, axpy3(beta, S, curl3(w, A)), 1.0 / alpha, kdot_over_k2(w, S));
             nw = so;
-          } else if (kind == 1) {
-            const double alpha = 1.0 / p.dt + w.k2 / (2.0 * p.Rm), beta = 1.0 / p.dt - w.k2 / (2.0 * p.Rm);
+          } else {
             so = proj_scale_minus(w, axpy3(beta, S, A), 1.0 / alpha, kdot_over_k2(w, S));
             nw = curl3(w, so);
-          } else {
-            so = proj_scale_minus(w, axpy3(-p.dt, A, S), 1.0, kdot_over_k2(w, S));
           }
         }
-        store3(p.o, sb, idx, so);
+        store3(p.o, 0, idx, so);
         *w0 = nw.x; *w1 = nw.y; *w2 = nw.z;
       }
     } else if (PH == 6) {
