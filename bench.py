@@ -195,8 +195,8 @@ def workload_config(name, gpus):
     return {"workload": "kinematic dynamo Npts=%d^3 (grid %d^3), Rm=%g, dt=%g, N_ITERS=%d, cost Final, discrete adjoint; "
                         "one step = f(X) + Grad_f(X), X=[B0,U]" % (N, M, Rm, dt, nit),
             "Npts": N, "N_ITERS": nit, "dof": 3 * N ** 3, "decomposition": "z/kx slabs over %d GPU(s)" % gpus,
-            "cache": "working set (snapshot store %.1f GB + 6 pencil fields) far larger than the 126 MB L2; no explicit flush"
-                     % ((nit + 1) * 3 * (N // 2) * (N - 1) * N * 16 / 1e9)}
+            "cache": "working set (x-spectral snapshot store %.1f GB over the GPUs + pencil fields) far larger than the 126 MB L2; no explicit flush"
+                     % ((nit + 1) * 3 * (N // 2) * M * M * 16 / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------------------------

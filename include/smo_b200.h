@@ -77,10 +77,15 @@ int smo_sh23_prep_host(smo_sh23_t* h, const double* X_host, int batch, double dt
 int smo_kdyn_create(smo_kdyn_t** h, int Npts, double L, int rank, int nranks, void* nccl_comm);
 int smo_kdyn_destroy(smo_kdyn_t* h);
 /* local sizes: elements of one grid component (M*M*nz doubles), of one coefficient component (complex128),
- * and bytes of the snapshot store for n_iters steps = (n_iters+1)*3*coef_elems*16 (GEN_BUFFER, KD:319-355) */
+ * and bytes of the snapshot store for n_iters steps (GEN_BUFFER, KD:319-355).  The store is opaque: forward states are
+ * kept as x-spectra on the z-slab (the form the adjoint x pass consumes: (n_iters+1) * 3 * (Npts/2)*M*nz complex) plus
+ * the coefficients of the final state; smo_kdyn_snapshot_coef converts a stored state back to coefficients. */
 size_t smo_kdyn_grid_elems(const smo_kdyn_t* h);
 size_t smo_kdyn_coef_elems(const smo_kdyn_t* h);
 size_t smo_kdyn_snapshot_bytes(const smo_kdyn_t* h, int n_iters);
+size_t smo_kdyn_segment_bytes(const smo_kdyn_t* h, int every);
+/* coefficients [3][coef_elems] of stored state n (0..n_iters) of a filled snapshot store (inspection / tests) */
+int smo_kdyn_snapshot_coef(smo_kdyn_t* h, const void* snaps_dev, int n_iters, int n, void* coef_dev, void* stream);
 /* Replaces FWD_Solve_IVP_Lin (KD:529-689), Cost_function="Final".  B0_dev, U_dev: [3][grid_elems] local slabs.
  * snaps_dev out.  J_host out: this rank's share of mean_grid(|B_N|^2) (sum over ranks = J; reference returns -J). */
 int smo_kdyn_forward(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, double Rm, double dt, int n_iters,
@@ -92,8 +97,8 @@ int smo_kdyn_adjoint(smo_kdyn_t* h, double Rm, double dt, int n_iters, const voi
                      double* gradU_dev, int flags, void* stream);
 /* Checkpointed forms of the two calls above (two-level, revolve style; for grids whose n_iters+1 states exceed HBM, e.g.
  * 256^3 x 1000 steps = 401 GB).  The forward solve keeps the states 0, every, 2*every, ... and N in ckpt_dev
- * (smo_kdyn_checkpoint_bytes); the adjoint sweep recomputes one segment at a time into seg_dev
- * (smo_kdyn_snapshot_bytes(h, every) bytes): at most n_iters - every extra forward steps.  Same results bit for bit. */
+ * (smo_kdyn_checkpoint_bytes, coefficient form); the adjoint sweep recomputes one segment at a time into seg_dev
+ * (smo_kdyn_segment_bytes(h, every) bytes, x-spectral form): at most n_iters extra forward steps.  Same results bit for bit. */
 size_t smo_kdyn_checkpoint_bytes(const smo_kdyn_t* h, int n_iters, int every);
 int smo_kdyn_forward_ckpt(smo_kdyn_t* h, const double* B0_dev, const double* U_dev, double Rm, double dt, int n_iters,
                           int every, void* ckpt_dev, double* J_host, int flags, void* stream);

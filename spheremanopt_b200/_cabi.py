@@ -38,6 +38,8 @@ SIGNATURES = {
     "smo_kdyn_grid_elems": (sz, [vp]),
     "smo_kdyn_coef_elems": (sz, [vp]),
     "smo_kdyn_snapshot_bytes": (sz, [vp, i32]),
+    "smo_kdyn_segment_bytes": (sz, [vp, i32]),
+    "smo_kdyn_snapshot_coef": (i32, [vp, vp, i32, i32, vp, vp]),
     "smo_kdyn_forward": (i32, [vp, dp, dp, f64, f64, i32, vp, C.POINTER(f64), i32, vp]),
     "smo_kdyn_adjoint": (i32, [vp, f64, f64, i32, vp, dp, dp, i32, vp]),
     "smo_kdyn_prep": (i32, [vp, dp, dp, f64, f64, i32, dp, vp]),
@@ -72,7 +74,6 @@ SIGNATURES = {
 
 SMO_ADJOINT_CONTINUOUS = 1
 SMO_COST_INTEGRATED = 2
-SMO_OPT_FUSED_Z = 1
 SMO_OPT_KERNEL_SYNC = 2
 SMO_OPT_PEER_PULL = 3
 

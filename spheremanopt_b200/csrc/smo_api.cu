@@ -452,7 +452,6 @@ struct smo_kdyn {
   // filled" (A, signalled by the forward y pass), [2MAXP..3MAXP) "p1t filled" (B, signalled by the z kernels)
   int inkernel_sync; unsigned long long epochA, epochB; unsigned int* counters;
   int peer_pull;                // 0 (default, measured faster on 2 B200): producers push; 1: consumers pull from the peers' buffers
-  int fused_z;                  // 1 (default): forward-z + implicit update + inverse-z of a time step in one kernel (zstep.cuh)
 };
 
 enum { PK_Z = 1, PK_Y = 2, PK_X = 3, PK_EPI = 4, PK_A2A = 5, PK_XA = 6, PK_ZS = 7 };
@@ -571,8 +570,10 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 #endif
 // ---- CUDA graphs ----------------------------------------------------------------------------------------------
 struct GraphKey {
-  int kind, n, opts; const void* p0; const void* p1; double Rm, dt;
-  bool operator==(const GraphKey& o) const { return kind == o.kind && n == o.n && opts == o.opts && p0 == o.p0 && p1 == o.p1 && Rm == o.Rm && dt == o.dt; }
+  int kind, n, opts; const void* p0; const void* p1; const void* p2; double Rm, dt;
+  bool operator==(const GraphKey& o) const {
+    return kind == o.kind && n == o.n && opts == o.opts && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 && Rm == o.Rm && dt == o.dt;
+  }
 };
 #if !defined(SMO_EMUL)
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; unsigned long long nA, nB; long long nlaunch; size_t ev0, ev1; };
@@ -728,17 +729,19 @@ template <int M> struct KdOps {
       p.tiles_per_row = nzc / T; p.row_tiles = h->nz / T; p.tile0 = z0 / T; p.nwork = M * p.tiles_per_row;
     }
   }
-  static int x_fwd(smo_kdyn* h, cplx* const* io, rt_stream st, int z0 = 0, int nzc = -1) {
+  // forward: x-spectra of B (the snapshot slot or the work arrays) in, x-spectra of U x B out (work arrays)
+  static int x_fwd(smo_kdyn* h, cplx* const* bp2, rt_stream st, int z0 = 0, int nzc = -1) {
     XFParams p; xffill(p, h, 4, z0, nzc);
-    for (int f = 0; f < 3; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
+    for (int f = 0; f < 3; ++f) { p.sin[f] = bp2[f]; p.sout[f] = h->p2[f]; }
     prof_begin(h, PK_X, st);
     int rc = launch<XFused<F, X_FWD>>(p, st);
     prof_end(h, PK_X, st);
     return rc;
   }
-  static int x_adj(smo_kdyn* h, cplx* const* io, rt_stream st, int z0 = 0, int nzc = -1) {
+  // adjoint: x-spectra of curl G (work arrays) and of the forward state B_f (read straight from its snapshot slot) in
+  static int x_adj(smo_kdyn* h, cplx* const* bfp2, rt_stream st, int z0 = 0, int nzc = -1) {
     XFParams p; xffill(p, h, 4, z0, nzc);
-    for (int f = 0; f < 6; ++f) { p.sin[f] = io[f]; p.sout[f] = io[f]; }
+    for (int f = 0; f < 3; ++f) { p.sin[f] = h->p2[f]; p.sout[f] = h->p2[f]; p.sin[3 + f] = bfp2[f]; }
     for (int c = 0; c < 3; ++c) p.sout[3 + c] = h->acc[c];    // (curl G) x B_f: summed over the sweep on the x-spectra
     p.accumulate = 1;
     prof_begin(h, PK_XA, st);
@@ -763,30 +766,30 @@ template <int M> struct KdOps {
     TRY(a2a(h, h->p1t, h->p1, 3, st));
     return fwd_z(h, h->p1, coef, 3, st);
   }
-  static int to_grid(smo_kdyn* h, const cplx* const* coef, double* grid, rt_stream st) {
+  static int to_grid(smo_kdyn* h, const cplx* const* coef, double* grid, rt_stream st) { return to_grid_via(h, coef, grid, h->p2, st); }
+  // the same, leaving the x-spectra (y- and z-padded) of the field in xs
+  static int to_grid_via(smo_kdyn* h, const cplx* const* coef, double* grid, cplx* const* xs, rt_stream st) {
     double* g[3] = {grid, grid + h->gsize, grid + 2 * h->gsize};
     if (h->peer_on) TRY(a2a(h, h->p1, h->p1t, 3, st));   // no peer still uses the buffers the z pass is about to fill
     TRY(inv_z(h, coef, h->p1, 3, st));
     TRY(a2a(h, h->p1, h->p1t, 3, st));
-    TRY(inv_y(h, h->p1t, h->p2, 3, st));
-    return x_c2r(h, h->p2, g, st);
+    TRY(inv_y(h, h->p1t, xs, 3, st));
+    return x_c2r(h, xs, g, st);
   }
   // fused z step (zstep.cuh): p1 -> [forward z FFT, implicit update of the state, inverse z FFT] -> p1
-  //   mode 0: state Bn -> Bnp1 (3 fields);  mode 1: state G, NU in place (6 fields), nxt = next forward snapshot
-  static int zstep(smo_kdyn* h, int mode, const cplx* const* Bn, cplx* const* Bnp1, const cplx* const* nxt, bool do_inv,
-                   double Rm, double dt, rt_stream st) {
+  //   mode 0: state Bn -> Bnp1, next operand Bnp1;  mode 1: state G in place, next operand curl G'
+  static int zstep(smo_kdyn* h, int mode, const cplx* const* Bn, cplx* const* Bnp1, bool do_inv, double Rm, double dt, rt_stream st) {
     ZParams p; memset(&p, 0, sizeof p);
     xs_wait(h, p.xs, XS_A);
     if (do_inv) xs_signal(h, p.xs, XS_B);
-    const int nf = mode == 0 ? 3 : 6;
+    const int nf = 3;
     for (int f = 0; f < nf; ++f) { p.in[f] = h->p1[f]; p.out[f] = h->p1[f]; }
     if (mode == 0) {
       for (int c = 0; c < 3; ++c) { p.b[c] = Bn[c]; p.o[c] = Bnp1[c]; }
     } else {
-      // triplet 0: G update from (curl G) x U, next operand curl G'; triplet 1: the next forward snapshot, inverse only
-      for (int c = 0; c < 3; ++c) { p.b[c] = h->G[c]; p.o[c] = h->G[c]; p.b[3 + c] = nxt ? nxt[c] : nullptr; }
+      for (int c = 0; c < 3; ++c) { p.b[c] = h->G[c]; p.o[c] = h->G[c]; }
     }
-    p.nsteps = 1; p.mode = mode; p.ntrip = (mode == 1 && do_inv) ? 2 : 1;
+    p.nsteps = 1; p.mode = mode; p.ntrip = 1;
     p.nlines = h->nkx * h->Nc; p.tiles = (p.nlines + TZS - 1) / TZS; p.nwork = p.tiles * p.ntrip;
     p.do_inv = do_inv ? 1 : 0;
     p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
@@ -804,74 +807,28 @@ template <int M> struct KdOps {
     prof_end(h, PK_ZS, st);
     return rc;
   }
-  // y -> fused x -> y part of a step: p1t (z-slab side) -> p1t
+  // y -> fused x -> y part of a step: p1t (z-slab side) -> p1t.  xs = x-spectra of the forward state: WRITTEN by the inverse
+  // y pass of a forward step (the snapshot slot of state n, or the work arrays), READ by the x pass of an adjoint step.
   // (with in-kernel hand-shakes the first y pass waits for "p1t filled", the last one signals "p1 filled")
-  static int yxy(smo_kdyn* h, int nf, rt_stream st) {
-    const int tile = nf == 3 ? TX : (TXA > TY ? TXA : TY);
-    const int nch = pick_chunks(h, nf == 3 ? h->chunks_fwd : h->chunks_adj, nf, tile);
+  static int yxy(smo_kdyn* h, int mode, cplx* const* xs, rt_stream st) {
+    const int nch = pick_chunks(h, mode == 0 ? h->chunks_fwd : h->chunks_adj, mode == 0 ? 3 : 6, TY > 4 ? TY : 4);
     const int nzc = h->nz / nch;
     for (int ch = 0; ch < nch; ++ch) {
-      const int z0 = ch * nzc;
-      TRY(inv_y(h, h->p1t, h->p2, nf, st, z0, nch > 1 ? nzc : -1, ch == 0 ? XS_B : XS_NONE));
-      if (nf == 3) TRY(x_fwd(h, h->p2, st, z0, nch > 1 ? nzc : -1));
-      else TRY(x_adj(h, h->p2, st, z0, nch > 1 ? nzc : -1));
-      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, nch > 1 ? nzc : -1, ch == nch - 1 ? XS_A : XS_NONE));
+      const int z0 = ch * nzc, zc = nch > 1 ? nzc : -1;
+      TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, st, z0, zc, ch == 0 ? XS_B : XS_NONE));
+      if (mode == 0) TRY(x_fwd(h, xs, st, z0, zc));
+      else TRY(x_adj(h, xs, st, z0, zc));
+      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, zc, ch == nch - 1 ? XS_A : XS_NONE));
     }
     return 0;
   }
+  // first half of a forward step only: x-spectra of the state whose z-padded form sits in p1t
+  static int y_only(smo_kdyn* h, cplx* const* xs, rt_stream st) { return inv_y(h, h->p1t, xs, 3, st, 0, -1, XS_B); }
   static void efill(EpiParams& p, smo_kdyn* h, double Rm, double dt, int flag) {
     memset(&p, 0, sizeof p);
     p.nsteps = 1; p.n = (long long)h->csize; p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
     p.kfac = h->kfac; p.Rm = Rm; p.dt = dt; p.flag = flag;
     p.nwork = (int)((p.n + 255) / 256);
-  }
-  // one CNAB1 step  Bn -> Bnp1 (both [3] coefficient arrays)
-  static int fwd_step(smo_kdyn* h, const cplx* const* Bn, cplx* const* Bnp1, double Rm, double dt, rt_stream st) {
-    TRY(inv_z(h, Bn, h->p1, 3, st));
-    TRY(a2a(h, h->p1, h->p1t, 3, st));
-    const int nch = pick_chunks(h, h->chunks_fwd, 3, TX);
-    const int nzc = h->nz / nch;
-    for (int ch = 0; ch < nch; ++ch) {
-      const int z0 = ch * nzc;
-      TRY(inv_y(h, h->p1t, h->p2, 3, st, z0, nch > 1 ? nzc : -1));
-      TRY(x_fwd(h, h->p2, st, z0, nch > 1 ? nzc : -1));
-      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, nch > 1 ? nzc : -1));
-    }
-    TRY(a2a(h, h->p1t, h->p1, 3, st));
-    TRY(fwd_z(h, h->p1, h->cw, 3, st));
-    EpiParams e; efill(e, h, Rm, dt, 0);
-    for (int c = 0; c < 3; ++c) { e.a[c] = h->cw[c]; e.b[c] = Bn[c]; e.o[c] = Bnp1[c]; }
-    prof_begin(h, PK_EPI, st);
-    int rc = launch<EpiKernel<EPI_FWD>>(e, st);
-    prof_end(h, PK_EPI, st);
-    return rc;
-  }
-  // one adjoint step using forward state Bf (coefficients)
-  static int adj_step(smo_kdyn* h, const cplx* const* Bf, double Rm, double dt, int flag, rt_stream st) {
-    const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], Bf[0], Bf[1], Bf[2]};
-    TRY(inv_z(h, in6, h->p1, 6, st));
-    TRY(a2a(h, h->p1, h->p1t, 6, st));
-    const int nch = pick_chunks(h, h->chunks_adj, 6, TXA > TY ? TXA : TY);
-    const int nzc = h->nz / nch;
-    for (int ch = 0; ch < nch; ++ch) {
-      const int z0 = ch * nzc;
-      TRY(inv_y(h, h->p1t, h->p2, 6, st, z0, nch > 1 ? nzc : -1));
-      TRY(x_adj(h, h->p2, st, z0, nch > 1 ? nzc : -1));
-      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, nch > 1 ? nzc : -1));
-    }
-    TRY(a2a(h, h->p1t, h->p1, 3, st));
-    TRY(fwd_z(h, h->p1, h->cw, 3, st));
-    EpiParams e; efill(e, h, Rm, dt, flag | 4);     // nu is accumulated by the x pass (flag 4: no nu update here)
-    for (int c = 0; c < 3; ++c) e.a[c] = h->cw[c];
-    for (int c = 0; c < 3; ++c) {
-      e.b[c] = h->G[c];
-      e.o[c] = h->G[c];
-      e.o2[c] = h->W[c]; e.o2[3 + c] = const_cast<cplx*>(Bf[c]);
-    }
-    prof_begin(h, PK_EPI, st);
-    int rc = launch<EpiKernel<EPI_ADJ>>(e, st);
-    prof_end(h, PK_EPI, st);
-    return rc;
   }
   static int compat(smo_kdyn* h, const cplx* const* BN, double Rm, double dt, int flag, rt_stream st) {
     EpiParams e; efill(e, h, Rm, dt, flag);
@@ -908,11 +865,6 @@ template <int M> struct KdOps {
   }
 };
 
-static void snap_ptrs(smo_kdyn* h, void* snaps, int n, cplx** out) {
-  cplx* s = (cplx*)snaps;
-  for (int c = 0; c < 3; ++c) out[c] = s + ((size_t)n * 3 + c) * h->csize;
-}
-
 // Runs body(stream) - a fixed sequence of kernel launches - eagerly, or (smo_kdyn_use_graph) replays it from a cached CUDA
 // graph: the first call with a given key runs eagerly, the second one captures and instantiates, later ones only launch.
 template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, rt_stream st, Body body) {
@@ -921,7 +873,7 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
   return body(st);
 #else
   // (per-kernel profiling events are captured as event-record nodes: every replay re-records the same events)
-  const bool can = h->use_graph && h->fused_z && (h->nranks == 1 || kernel_sync(h));
+  const bool can = h->use_graph && (h->nranks == 1 || kernel_sync(h));
   if (!can) return body(st);
   if (!h->graphs) {
     h->graphs = new GraphCache();
@@ -971,7 +923,26 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
   return 0;
 #endif
 }
-static int graph_opts(const smo_kdyn* h) { return (h->prof_which << 24) | (h->fused_z ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16); }
+static int graph_opts(const smo_kdyn* h) { return (h->prof_which << 24) | 1 | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16); }
+
+// ---- snapshot store ------------------------------------------------------------------------------------------------
+// Forward states are kept in the form the adjoint x pass consumes: their x-spectra on this rank's z-slab, [Nh][M][nz] per
+// component (y- and z-padded: 2.3 x the bytes of the coefficients).  The inverse y pass of forward step n writes them
+// straight into slot n - no extra traffic in the forward solve - and the adjoint sweep needs no z / y transform and no
+// transpose of the forward state at all.  Layout: n_iters + 1 slots of 3 * p2size, then the coefficients of the final
+// state (3 * csize; terminal condition of the adjoint).  Checkpoints (kd_*_ckpt) stay in coefficient form.
+static void snap_ptrs(smo_kdyn* h, void* snaps, int n, cplx** out) {     // coefficient-form slot n (checkpoint stores)
+  cplx* s = (cplx*)snaps;
+  for (int c = 0; c < 3; ++c) out[c] = s + ((size_t)n * 3 + c) * h->csize;
+}
+static void snap_xs(smo_kdyn* h, void* snaps, int n, cplx** out) {       // x-spectral slot n
+  cplx* s = (cplx*)snaps;
+  for (int c = 0; c < 3; ++c) out[c] = s + ((size_t)n * 3 + c) * h->p2size;
+}
+static void snap_final(smo_kdyn* h, void* snaps, int n_iters, cplx** out) {
+  cplx* s = (cplx*)snaps + (size_t)(n_iters + 1) * 3 * h->p2size;
+  for (int c = 0; c < 3; ++c) out[c] = s + (size_t)c * h->csize;
+}
 
 // loop bodies, templated on M ---------------------------------------------------------------------------------
 template <int M> static int kd_set_U(smo_kdyn* h, const double* U, rt_stream st) {
@@ -984,53 +955,54 @@ template <int M> static int kd_set_U(smo_kdyn* h, const double* U, rt_stream st)
   h->have_U = true;
   return 0;
 }
-// Time loop of the forward problem with the fused z step: the state travels  coefficients -> p1 -> p2 -> (x pass) -> p2
-// -> p1 -> [zstep: coefficients of step n+1 written to state(n+1), and already on their way back to p1].
-// state(n) returns the three coefficient arrays of step n.
-template <int M, class StateFn>
-static int kd_forward_loop(smo_kdyn* h, int n_steps, double Rm, double dt, StateFn state, rt_stream st) {
+// buffers of forward step n: coefficients of state n in, of state n+1 out, and where the x-spectra of state n go
+struct FwdStep { cplx* cin[3]; cplx* cout[3]; cplx* xs[3]; };
+// Time loop of the forward problem: 4 launches per step.  The state travels  coefficients -> p1 -> [y inverse] -> x-spectra
+// (snapshot slot) -> [fused x] -> [y forward] -> p1 -> [fused z step: coefficients of step n+1 written, and already on their
+// way back to p1].  tail_xs_only: the last "step" only produces the x-spectra of its state (snapshot of the final state).
+template <int M, class StepFn>
+static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double Rm, double dt, StepFn step, rt_stream st) {
   if (n_steps <= 0) return 0;
-  if (!h->fused_z) {
-    for (int n = 0; n < n_steps; ++n) TRY(KdOps<M>::fwd_step(h, state(n), state(n + 1), Rm, dt, st));
-    return 0;
-  }
-  // multi-GPU: the transposes are remote stores of the kernels themselves; their hand-shakes are either fused into the
-  // kernels (ks: producer signals at its end, consumer waits at its start) or separate barrier launches (a2a)
+  // multi-GPU: the transposes are remote stores / loads of the kernels themselves; their hand-shakes are either fused into
+  // the kernels (ks: producer signals at its end, consumer waits at its start) or separate barrier launches (a2a)
   const bool ks = kernel_sync(h);
   if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));     // every rank has left whatever used the pencil buffers before
-  GraphKey key; key.kind = 1; key.n = n_steps; key.opts = graph_opts(h); key.p0 = state(0)[0]; key.p1 = state(n_steps)[0]; key.Rm = Rm; key.dt = dt;
+  const FwdStep first = step(0), last = step(n_steps - 1);
+  GraphKey key; key.kind = tail_xs_only ? 3 : 1; key.n = n_steps; key.opts = graph_opts(h); key.p0 = first.xs[0]; key.p1 = last.cout[0];
+  key.p2 = first.cin[0]; key.Rm = Rm; key.dt = dt;    // (everything else a step touches follows from these by construction)
   return run_graphed(h, key, st, [&](rt_stream s) -> int {
-    TRY(KdOps<M>::inv_z(h, state(0), h->p1, 3, s, XS_B));
+    TRY(KdOps<M>::inv_z(h, first.cin, h->p1, 3, s, XS_B));
     if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, s));
     for (int n = 0; n < n_steps; ++n) {
-      TRY(KdOps<M>::yxy(h, 3, s));
+      const FwdStep b = step(n);
+      if (tail_xs_only && n == n_steps - 1) return KdOps<M>::y_only(h, b.xs, s);
+      TRY(KdOps<M>::yxy(h, 0, b.xs, s));
       if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, s));
       const bool more = n + 1 < n_steps;
-      TRY(KdOps<M>::zstep(h, 0, state(n), state(n + 1), nullptr, more, Rm, dt, s));
+      TRY(KdOps<M>::zstep(h, 0, b.cin, b.cout, more, Rm, dt, s));
       if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 3, s));
     }
     return 0;
   });
 }
-struct SnapState {
-  smo_kdyn* h; void* snaps; cplx* cur[2][3]; int flip;
-  cplx* const* operator()(int n) { flip ^= 1; snap_ptrs(h, snaps, n, cur[flip]); return cur[flip]; }
-};
-struct PingPong {
-  cplx** a; cplx** b;
-  cplx* const* operator()(int n) { return (n & 1) ? b : a; }
-};
+// coefficient state n of a plain time loop ping-pongs between two scratch triplets
+static void pingpong(cplx* const* a, cplx* const* b, int n, FwdStep& f) {
+  for (int c = 0; c < 3; ++c) { f.cin[c] = (n & 1) ? b[c] : a[c]; f.cout[c] = (n & 1) ? a[c] : b[c]; }
+}
 template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                                        void* snaps, double* J_host, rt_stream st) {
   TRY(kd_set_U<M>(h, U, st));
-  cplx* s0[3];
-  snap_ptrs(h, snaps, 0, s0);
-  TRY(KdOps<M>::to_coef(h, B0, s0, st));
-  SnapState state; state.h = h; state.snaps = snaps; state.flip = 0;
-  TRY((kd_forward_loop<M>(h, n_iters, Rm, dt, state, st)));
+  TRY(KdOps<M>::to_coef(h, B0, h->G, st));
+  auto step = [&](int n) { FwdStep f; pingpong(h->G, h->NU, n, f); snap_xs(h, snaps, n, f.xs); return f; };
+  // n_iters steps + the x-spectra of the final state (slot n_iters: continuous adjoint, and the cost below)
+  TRY((kd_forward_loop<M>(h, n_iters + 1, true, Rm, dt, step, st)));
+  const FwdStep fin = step(n_iters);
+  cplx* sf[3];
+  snap_final(h, snaps, n_iters, sf);
+  for (int c = 0; c < 3; ++c) TRY(rt_d2d(sf[c], fin.cin[c], sizeof(cplx) * h->csize, st));
   // Cost "Final": J = mean over the dealiased grid of |B^N|^2 (FWD_Solve_KDyn.py:622, 671-673)
-  snap_ptrs(h, snaps, n_iters, s0);
-  TRY(KdOps<M>::to_grid(h, s0, h->gwork, st));
+  double* g[3] = {h->gwork, h->gwork + h->gsize, h->gwork + 2 * h->gsize};
+  TRY(KdOps<M>::x_c2r(h, fin.xs, g, st));
   const double scale = 1.0 / ((double)M * M * M);
   prof_collect(h, st);
   return smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st);
@@ -1039,35 +1011,31 @@ template <int M> static int kd_prep(smo_kdyn* h, const double* B0, const double*
                                     double* out, rt_stream st) {
   TRY(kd_set_U<M>(h, U, st));
   // ping-pong between G and NU as coefficient state (no snapshots kept)
-  PingPong state; state.a = h->G; state.b = h->NU;
   TRY(KdOps<M>::to_coef(h, B0, h->G, st));
-  TRY((kd_forward_loop<M>(h, n_iters + 1, Rm, dt, state, st)));
-  return KdOps<M>::to_grid(h, state(n_iters + 1), out, st);
+  auto step = [&](int n) { FwdStep f; pingpong(h->G, h->NU, n, f); for (int c = 0; c < 3; ++c) f.xs[c] = h->p2[c]; return f; };
+  TRY((kd_forward_loop<M>(h, n_iters + 1, false, Rm, dt, step, st)));
+  return KdOps<M>::to_grid(h, step(n_iters + 1).cin, out, st);
 }
-// Adjoint time loop over `count` forward states, state(i) = coefficients of the i-th state the sweep linearises about
-// (descending in time).  G, nu (and W = curl G on entry) live in the handle and persist between calls, so a checkpointed
-// sweep can call this once per recomputed segment.
+// Adjoint time loop over `count` forward states, state(i) = x-spectra of the i-th state the sweep linearises about
+// (descending in time).  G, the running sum of the gradient integrand (and W = curl G on entry) live in the handle and
+// persist between calls, so a checkpointed sweep can call this once per recomputed segment.  3 transforms in, 3 out.
+struct XsPtr { cplx* p[3]; };
 template <int M, class StateFn>
 static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn state, rt_stream st) {
   if (count <= 0) return 0;
-  if (!h->fused_z) {
-    for (int i = 0; i < count; ++i) TRY(KdOps<M>::adj_step(h, state(i), Rm, dt, 0, st));
-    return 0;
-  }
   const bool ks = kernel_sync(h);
-  if (ks) TRY(a2a(h, h->p1, h->p1t, 6, st));
-  GraphKey key; key.kind = 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0)[0]; key.p1 = state(count - 1)[0]; key.Rm = Rm; key.dt = dt;
+  if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));
+  GraphKey key; key.kind = 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0).p[0]; key.p1 = state(count - 1).p[0]; key.p2 = nullptr; key.Rm = Rm; key.dt = dt;
   return run_graphed(h, key, st, [&](rt_stream q) -> int {
-    cplx* const* s = state(0);
-    const cplx* in6[6] = {h->W[0], h->W[1], h->W[2], s[0], s[1], s[2]};
-    TRY(KdOps<M>::inv_z(h, in6, h->p1, 6, q, XS_B));
-    if (!ks) TRY(a2a(h, h->p1, h->p1t, 6, q));
+    TRY(KdOps<M>::inv_z(h, h->W, h->p1, 3, q, XS_B));
+    if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, q));
     for (int i = 0; i < count; ++i) {
-      TRY(KdOps<M>::yxy(h, 6, q));
-      if (!ks) TRY(a2a(h, h->p1t, h->p1, 6, q));
+      const XsPtr bf = state(i);
+      TRY(KdOps<M>::yxy(h, 1, bf.p, q));
+      if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, q));
       const bool more = i + 1 < count;
-      TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more ? state(i + 1) : nullptr, more, Rm, dt, q));
-      if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 6, q));
+      TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more, Rm, dt, q));
+      if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 3, q));
     }
     return 0;
   });
@@ -1080,42 +1048,44 @@ template <int M> static int kd_adjoint_finish(smo_kdyn* h, double Rm, double dt,
   prof_collect(h, st);
   return 0;
 }
-template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_iters, const void* snaps, double* gB,
+template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_iters, const void* snapsc, double* gB,
                                        double* gU, int flags, rt_stream st) {
   const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
+  void* snaps = const_cast<void*>(snapsc);
   cplx* s[3];
-  snap_ptrs(h, const_cast<void*>(snaps), n_iters, s);
+  snap_final(h, snaps, n_iters, s);
   TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
   TRY(KdOps<M>::acc_begin(h, st));
   // adjoint step m linearises about snapshot idx(m): snapshot_index -1-m (continuous) / -2-m (discrete)
-  SnapState sn; sn.h = h; sn.snaps = const_cast<void*>(snaps); sn.flip = 0;
-  auto state = [&](int m) { return sn(cont ? (n_iters - m) : (n_iters - 1 - m)); };
+  auto state = [&](int m) { XsPtr x; snap_xs(h, snaps, cont ? (n_iters - m) : (n_iters - 1 - m), x.p); return x; };
   TRY((kd_adjoint_loop<M>(h, n_iters, Rm, dt, state, st)));
   return kd_adjoint_finish<M>(h, Rm, dt, cont, gB, gU, st);
 }
 
 // ---- checkpointed sweeps (two-level, revolve style) -----------------------------------------------------------------
-// The forward solve keeps only the states 0, every, 2*every, ... and the final state N (slot ceil(N/every)); the adjoint
-// walks the segments backwards, recomputing the states of one segment into a buffer of every+1 slots before it sweeps
-// them.  Memory: ceil(N/every) + 1 + every + 1 states instead of N + 1; extra work: at most N - every forward steps
-// (recompute factor rho < 1 of one forward solve).
+// The forward solve keeps only the coefficients of the states 0, every, 2*every, ... and of the final state N (slot
+// ceil(N/every)); the adjoint walks the segments backwards, recomputing the x-spectra of the states of one segment into a
+// buffer of every+1 slots before it sweeps them.  Memory: ceil(N/every) + 1 coefficient states + every + 1 x-spectral
+// states instead of N + 1; extra work: at most N forward steps (recompute factor rho <= 1 of one forward solve).
 static int ckpt_slots(int n_iters, int every) { return (n_iters + every - 1) / every + 1; }
 static int ckpt_slot_of(int n, int n_iters, int every) { return n == n_iters ? ckpt_slots(n_iters, every) - 1 : n / every; }
-struct CkptState {   // forward solve: checkpoints go to their slots, everything else to two scratch states
-  smo_kdyn* h; void* ck; int n_iters, every; cplx* cur[2][3]; int flip;
-  cplx* const* operator()(int n) {
-    if (n % every == 0 || n == n_iters) { flip ^= 1; snap_ptrs(h, ck, ckpt_slot_of(n, n_iters, every), cur[flip]); return cur[flip]; }
-    return (n & 1) ? h->NU : h->G;
-  }
-};
+// coefficient state n of the checkpointing forward solve: its checkpoint slot, or one of two scratch states
+static void ckpt_coef(smo_kdyn* h, void* ck, int n, int n_iters, int every, cplx** out) {
+  if (n % every == 0 || n == n_iters) { snap_ptrs(h, ck, ckpt_slot_of(n, n_iters, every), out); return; }
+  for (int c = 0; c < 3; ++c) out[c] = (n & 1) ? h->NU[c] : h->G[c];
+}
 template <int M> static int kd_forward_ckpt(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                                             int every, void* ck, double* J_host, rt_stream st) {
   TRY(kd_set_U<M>(h, U, st));
   cplx* s0[3];
   snap_ptrs(h, ck, 0, s0);
   TRY(KdOps<M>::to_coef(h, B0, s0, st));
-  CkptState state; state.h = h; state.ck = ck; state.n_iters = n_iters; state.every = every; state.flip = 0;
-  TRY((kd_forward_loop<M>(h, n_iters, Rm, dt, state, st)));
+  auto step = [&](int n) {
+    FwdStep f; ckpt_coef(h, ck, n, n_iters, every, f.cin); ckpt_coef(h, ck, n + 1, n_iters, every, f.cout);
+    for (int c = 0; c < 3; ++c) f.xs[c] = h->p2[c];
+    return f;
+  };
+  TRY((kd_forward_loop<M>(h, n_iters, false, Rm, dt, step, st)));
   snap_ptrs(h, ck, ckpt_slot_of(n_iters, n_iters, every), s0);
   TRY(KdOps<M>::to_grid(h, s0, h->gwork, st));
   const double scale = 1.0 / ((double)M * M * M);
@@ -1133,20 +1103,35 @@ template <int M> static int kd_adjoint_ckpt(smo_kdyn* h, double Rm, double dt, i
   const int nseg = (n_iters + every - 1) / every;
   for (int k = nseg - 1; k >= 0; --k) {
     const int n0 = k * every, n1 = (n0 + every < n_iters) ? n0 + every : n_iters;   // the segment holds the states n0 .. n1
-    // states the sweep needs from this segment: n1-1 .. n0 (discrete) or n1 .. n0+1 (continuous)
-    const int steps = cont ? (n1 - n0) : (n1 - n0 - 1);            // forward steps to recompute from checkpoint n0
-    cplx* c0[3]; cplx* cur[2][3]; int flip = 0;
+    // states the sweep needs from this segment: n1-1 .. n0 (discrete) or n1 .. n0+1 (continuous).  Recompute from checkpoint
+    // n0: full steps up to the last state needed, of which only the x-spectra are produced (tail); scratch coefficients in cw
+    const int last = cont ? (n1 - n0) : (n1 - n0 - 1);
+    cplx* c0[3];
     snap_ptrs(h, ck, k, c0);
-    auto segstate = [&](int j) -> cplx* const* {                    // state n0 + j
-      if (j == 0) return c0;
-      flip ^= 1; snap_ptrs(h, seg, j, cur[flip]); return cur[flip];
+    auto step = [&](int j) {
+      FwdStep f;
+      for (int c = 0; c < 3; ++c) {
+        f.cin[c] = (j == 0) ? c0[c] : h->cw[(j & 1) ? 3 + c : c];
+        f.cout[c] = h->cw[(j & 1) ? c : 3 + c];
+      }
+      snap_xs(h, seg, j, f.xs);
+      return f;
     };
-    TRY((kd_forward_loop<M>(h, steps, Rm, dt, segstate, st)));
-    if (k != nseg - 1 && h->fused_z) TRY(KdOps<M>::curl_G(h, Rm, dt, st));   // W = curl G (the fused step keeps it on chip only)
-    auto sweep = [&](int i) -> cplx* const* { return segstate(cont ? (n1 - n0 - i) : (n1 - n0 - 1 - i)); };
+    TRY((kd_forward_loop<M>(h, last + 1, true, Rm, dt, step, st)));
+    if (k != nseg - 1) TRY(KdOps<M>::curl_G(h, Rm, dt, st));   // W = curl G (the fused step keeps it on chip only)
+    auto sweep = [&](int i) { XsPtr x; snap_xs(h, seg, last - i, x.p); return x; };
     TRY((kd_adjoint_loop<M>(h, n1 - n0, Rm, dt, sweep, st)));
   }
   return kd_adjoint_finish<M>(h, Rm, dt, cont, gB, gU, st);
+}
+// inspection: coefficients of stored state n (tests, SnapshotStore['A_fwd'])
+template <int M> static int kd_snapshot_coef(smo_kdyn* h, void* snaps, int n, cplx* const* coef, rt_stream st) {
+  cplx* xs[3];
+  snap_xs(h, snaps, n, xs);
+  if (h->peer_on) TRY(a2a(h, h->p1t, h->p1, 3, st));
+  TRY(KdOps<M>::fwd_y(h, xs, h->p1t, 3, st));
+  TRY(a2a(h, h->p1t, h->p1, 3, st));
+  return KdOps<M>::fwd_z(h, h->p1, coef, 3, st);
 }
 
 #define KD_DISPATCH(h, CALL, ...)                                                                  \
@@ -1190,7 +1175,6 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0;
   for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
   for (int s2 = 0; s2 < MAXP; ++s2) h->peer_flags[s2] = nullptr;
-  h->fused_z = 1;
   h->chunks_fwd = h->chunks_adj = 1;    // off by default (measured slower at 128^3: the passes are not HBM-bound enough to gain)
   h->hB = h->hU = h->hGB = h->hGU = nullptr; h->snaps = nullptr; h->cap_snap = 0;
   h->tw = nullptr; h->gwork = nullptr; h->vwork = nullptr;
@@ -1258,7 +1242,10 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
 extern "C" size_t smo_kdyn_grid_elems(const smo_kdyn_t* h) { return h ? h->gsize : 0; }
 extern "C" size_t smo_kdyn_coef_elems(const smo_kdyn_t* h) { return h ? h->csize : 0; }
 extern "C" size_t smo_kdyn_snapshot_bytes(const smo_kdyn_t* h, int n_iters) {
-  return h ? sizeof(cplx) * 3 * h->csize * (size_t)(n_iters + 1) : 0;
+  return h ? sizeof(cplx) * 3 * (h->p2size * (size_t)(n_iters + 1) + h->csize) : 0;
+}
+extern "C" size_t smo_kdyn_segment_bytes(const smo_kdyn_t* h, int every) {
+  return h ? sizeof(cplx) * 3 * h->p2size * (size_t)(every + 1) : 0;
 }
 static int kd_args(smo_kdyn* h, double Rm, double dt, int n_iters, int flags, const char* who) {
   if (!h) return fail(SMO_E_ARG, "%s: null handle", who);
@@ -1305,6 +1292,12 @@ extern "C" int smo_kdyn_adjoint_ckpt(smo_kdyn_t* h, double Rm, double dt, int n_
   if (!h->have_U) return fail(SMO_E_STATE, "smo_kdyn_adjoint_ckpt: no preceding forward solve on this handle");
   rt_stream st = (rt_stream)stream;
   KD_DISPATCH(h, kd_adjoint_ckpt, h, Rm, dt, n_iters, every, ckpt, seg, gB, gU, flags, st)
+}
+extern "C" int smo_kdyn_snapshot_coef(smo_kdyn_t* h, const void* snaps, int n_iters, int n, void* coef, void* stream) {
+  if (!h || !snaps || !coef || n < 0 || n > n_iters) return fail(SMO_E_ARG, "smo_kdyn_snapshot_coef: bad argument");
+  rt_stream st = (rt_stream)stream;
+  cplx* c[3] = {(cplx*)coef, (cplx*)coef + h->csize, (cplx*)coef + 2 * h->csize};
+  KD_DISPATCH(h, kd_snapshot_coef, h, const_cast<void*>(snaps), n, c, st)
 }
 extern "C" int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid, void* coef, void* stream) {
   if (!h || !grid || !coef) return fail(SMO_E_ARG, "smo_kdyn_to_coef: bad argument");
@@ -1391,7 +1384,6 @@ extern "C" int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj
 extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
   if (!h) return fail(SMO_E_ARG, "smo_kdyn_set_option: null handle");
   switch (key) {
-    case SMO_OPT_FUSED_Z: h->fused_z = value ? 1 : 0; return 0;
     case SMO_OPT_KERNEL_SYNC: h->inkernel_sync = value ? 1 : 0; return 0;
     case SMO_OPT_PEER_PULL: h->peer_pull = value ? 1 : 0; return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic

@@ -10,9 +10,9 @@
 //
 // A work item is a *triplet*: the three vector components of T adjacent z lines (a z line = all kz of one (kx, ky)).
 //   forward step : 1 triplet per tile  - in = to_p1(U x B^n),        state B^n -> B^{n+1},   next operand B^{n+1}
-//   adjoint step : 2 triplets per tile - in = to_p1((curl G) x U),   state G -> G',          next operand curl G'
-//                                        no input, no update:                               next operand B_f (next snapshot)
-//   (the gradient integrand nu is accumulated on the x-spectra by the x pass and transformed once after the sweep)
+//   adjoint step : 1 triplet per tile  - in = to_p1((curl G) x U),   state G -> G',          next operand curl G'
+//   (the gradient integrand nu is accumulated on the x-spectra by the x pass and transformed once after the sweep; the
+//    forward state B_f is read by the x pass in x-spectral form straight from its snapshot slot)
 // Thread (f, t, jj): component f, line t, stage thread jj < RT.  With RT dividing 32 all exchanges of a line stay
 // inside one warp, so only the two barriers around the pointwise update (which mixes the three components) are
 // CTA-wide; everything else is a __syncwarp (smo_common.cuh: sync_after).
@@ -31,11 +31,10 @@ namespace smo {
 struct ZParams {
   const cplx* in[MAXF];     // p1 inputs (kx-slab side), one per field
   cplx* out[MAXF];          // p1 outputs (local buffer; peer buffers below when peer_mode != 0)
-  const cplx* b[MAXF];      // coefficient state in  : forward B^n[3]    | adjoint G[3], then the forward-state snapshot
-                            //                         the next adjoint step linearises about [3]
+  const cplx* b[MAXF];      // coefficient state in  : forward B^n[3]    | adjoint G[3]
   cplx* o[MAXF];            // coefficient state out : forward B^{n+1}[3] | adjoint G'[3]
   int nwork, nsteps;        // nwork = tiles * ntrip
-  int ntrip, mode;          // mode 0: forward CNAB1 step (ntrip 1); mode 1: adjoint step (ntrip 2, or 1 when nothing follows)
+  int ntrip, mode;          // mode 0: forward CNAB1 step; mode 1: adjoint step; ntrip = triplets per tile (1)
   int nlines, tiles;        // z lines of this rank = nkx*Nc
   int do_inv;               // 0: last step of a loop, nothing follows on the grid side
   int Nc, Pc, kmax, kx0;
@@ -94,7 +93,7 @@ template <class F, int T_> struct ZStep {
     split_tid(c.tid, f, t, jj);
     decode(p, work, tile, trip);
     const int b = tile * T + t;
-    if (b >= p.nlines || trip == 1) return;      // the second triplet of an adjoint step has no pencil input
+    if (b >= p.nlines) return;
     cplx* Ld = land(c.smem) + (f * T + t) * M;
     const cplx* src = p.in[3 * trip + f] + (long long)b * p.line_stride;
     if (p.seglen <= 0) {
@@ -142,7 +141,7 @@ template <class F, int T_> struct ZStep {
     decode(p, work, tile, trip);
     const int b = tile * T + t;
     const bool live = b < p.nlines;
-    const bool fwd = live && trip == 0;          // this triplet has a pencil input to transform and a state to update
+    const bool fwd = live;
     cplx* Ld = land(c.smem) + (f * T + t) * M;
     cplx* Wk = wrk(c.smem) + (f * T + t) * XP;
     if (PH == 0) {
@@ -195,7 +194,7 @@ template <class F, int T_> struct ZStep {
       }
     } else if (PH == 5) {
       // pointwise implicit update of the three components at (line, kz); consecutive threads -> consecutive kz
-      const int kind = (p.mode == 0) ? 0 : 1 + trip;      // 0 forward step, 1 adjoint G, 2 next forward snapshot (copy only)
+      const int kind = p.mode;                            // 0 forward step, 1 adjoint G
       cplx* Wt = wrk(c.smem);
       for (int e = c.tid; e < T * PC; e += THREADS) {
         const int tt = e / PC, iz = e - tt * PC;
@@ -206,7 +205,6 @@ template <class F, int T_> struct ZStep {
         cplx* w2 = Wt + (2 * T + tt) * XP + iz;
         const cplx* Ss = stl(c.smem) + tt * PC + iz;
         C3 S; S.x = Ss[0]; S.y = Ss[T * PC]; S.z = Ss[2 * T * PC];
-        if (kind == 2) { *w0 = S.x; *w1 = S.y; *w2 = S.z; continue; }
         const int ix = bl / p.Nc, iy = bl - ix * p.Nc;
         Wave w;
         w.kx = p.kfac * (double)(p.kx0 + ix);

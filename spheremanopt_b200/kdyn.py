@@ -150,9 +150,11 @@ class Domain:
 
 
 class SnapshotStore(dict):
-    """Device-resident replacement of ``{'A_fwd','B_fwd','C_fwd'}`` (KD:347-355): [N_SUB_ITERS+1][3][nkx][Nc][Nc+1]
-    complex128 in HBM (this rank's kx-slab).  ``['A_fwd']`` etc. return host copies in the reference's
-    [Npts/2, Npts-1, Npts-1, N_SUB_ITERS+1] orientation (single rank only), for inspection."""
+    """Device-resident replacement of ``{'A_fwd','B_fwd','C_fwd'}`` (KD:347-355).  Opaque HBM store: every forward state is
+    kept as x-spectra on this rank's z-slab ([N_SUB_ITERS+1][3][Npts/2][M][nz] complex128: what the adjoint x pass reads,
+    written for free by the forward solve's y pass) plus the coefficients of the final state.  ``['A_fwd']`` etc. convert
+    back and return host copies in the reference's [Npts/2, Npts-1, Npts-1, N_SUB_ITERS+1] orientation (single rank
+    only), for inspection."""
 
     def __init__(self, domain, n_iters):
         super().__init__()
@@ -167,8 +169,13 @@ class SnapshotStore(dict):
     def __getitem__(self, key):
         c = {'A_fwd': 0, 'B_fwd': 1, 'C_fwd': 2}[key]
         d = self.domain
-        a = self.buf.view(self.n_iters + 1, 3, d.nkx, d.Nc, d.Nc + 1)[:, c, :, :, :d.Nc]
-        return np.transpose(a.cpu().numpy(), (1, 2, 3, 0)).copy()
+        out = np.zeros((d.nkx, d.Nc, d.Nc, self.n_iters + 1), dtype=np.complex128)
+        coef = torch.zeros(3 * d.csize, dtype=torch.complex128, device=d.device)
+        with torch.cuda.device(d.device):
+            for n in range(self.n_iters + 1):
+                _cabi.check(d.lib, d.lib.smo_kdyn_snapshot_coef(d.h, self.ptr(), self.n_iters, n, coef.data_ptr(), _stream_ptr()))
+                out[..., n] = coef.view(3, d.nkx, d.Nc, d.Nc + 1)[c, :, :, :d.Nc].cpu().numpy()
+        return out
 
 
 class CheckpointStore(dict):
@@ -183,11 +190,11 @@ class CheckpointStore(dict):
         lib = domain.lib
         self.buf = torch.zeros(lib.smo_kdyn_checkpoint_bytes(domain.h, self.n_iters, self.every) // 16, dtype=torch.complex128,
                                device=domain.device)
-        self.seg = torch.zeros(lib.smo_kdyn_snapshot_bytes(domain.h, self.every) // 16, dtype=torch.complex128, device=domain.device)
+        self.seg = torch.zeros(lib.smo_kdyn_segment_bytes(domain.h, self.every) // 16, dtype=torch.complex128, device=domain.device)
         self.valid = False
         nseg = (self.n_iters + self.every - 1) // self.every
         self.states_held = nseg + 1 + self.every + 1
-        self.rho = sum(max(min(self.every, self.n_iters - k * self.every) - 1, 0) for k in range(nseg)) / max(self.n_iters, 1)
+        self.rho = sum(max(min(self.every, self.n_iters - k * self.every) - 1, 0) for k in range(nseg)) / max(self.n_iters, 1)   # full steps recomputed
 
     def ptr(self):
         return self.buf.data_ptr()

@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mp_parity.py
 
 Every transport is exercised: peer-memory transposes with in-kernel hand-shakes (default), peer-memory transposes with
-barrier launches, grouped ncclSend/ncclRecv; fused and unfused z step; host vectors (Mode H) and DevVec (Mode D).
+barrier launches, grouped ncclSend/ncclRecv; CUDA-graph replay; host vectors (Mode H) and DevVec (Mode D).
 Rank 0 prints "MP_PARITY OK" on success.  tests/test_gpu_multi.py wraps this for pytest -m gpu on boxes with >= 2 GPUs.
 """
 import os
@@ -38,11 +38,10 @@ def main():
         D = okd.GEN_BUFFER(Npts, od, nit)
         fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
         go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
-        # (peer memory, in-kernel hand-shakes, fused z step, pull transposes)
-        for peer, ksync, fused, pull in ((True, 1, 1, 1), (True, 0, 1, 1), (True, 1, 0, 1), (True, 1, 1, 0), (True, 0, 0, 0), (False, 0, 1, 0)):
+        # (peer memory, in-kernel hand-shakes, graph replay, pull transposes)
+        for peer, ksync, fused, pull in ((True, 1, 1, 1), (True, 0, 0, 1), (True, 1, 0, 0), (True, 1, 1, 0), (True, 0, 0, 0), (False, 0, 0, 0)):
             dom = kdyn.Domain(Npts, device="cuda:%d" % local, peer_memory=peer)
             dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_KERNEL_SYNC, ksync)
-            dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_FUSED_Z, fused)
             dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_PEER_PULL, pull)
             store = kdyn.GEN_BUFFER(Npts, dom, nit)
             if peer and ksync and fused:
@@ -60,7 +59,7 @@ def main():
             e.append(abs(ip - okd.Inner_Prod_3(go[0], B0, od)) / abs(okd.Inner_Prod_3(go[0], B0, od)))
             worst = max(worst, max(e))
             if rank == 0:
-                print("P=%d N=%d peer=%d ksync=%d fused_z=%d pull=%d: max rel.err %.2e" % (world, Npts, peer, ksync, fused, pull, max(e)), flush=True)
+                print("P=%d N=%d peer=%d ksync=%d graph=%d pull=%d: max rel.err %.2e" % (world, Npts, peer, ksync, fused, pull, max(e)), flush=True)
             del dom, store
     ok = torch.tensor([1 if worst <= TOL else 0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)

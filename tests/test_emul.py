@@ -73,8 +73,11 @@ def test_kdyn_emulated(L, Npts, nit):
     fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
     go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
     assert abs(-J.value - fo) <= TOL * abs(fo)
-    s = snaps.reshape(nit + 1, 3, od.Nh, od.Nc, od.Nc + 1)[..., :od.Nc]
-    assert relerr(np.transpose(s[:, 0], (1, 2, 3, 0)), D['A_fwd']) <= TOL
+    sc = np.zeros((3, csz), dtype=complex)
+    for n in (0, 1, nit):      # stored states (x-spectral form) converted back to coefficients
+        emul.check(L.smo_kdyn_snapshot_coef(h, emul.ptr(snaps), nit, n, emul.ptr(sc), None))
+        for c, key in enumerate(('A_fwd', 'B_fwd', 'C_fwd')):
+            assert relerr(sc[c].reshape(od.Nh, od.Nc, od.Nc + 1)[..., :od.Nc], D[key][..., n]) <= TOL
     assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
     if Npts == 24:
         gBc, gUc = np.zeros(3 * gsz), np.zeros(3 * gsz)
@@ -104,7 +107,7 @@ def test_kdyn_checkpointed_emulated(L, every, cont):
     gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
     emul.check(L.smo_kdyn_adjoint(h, Rm, dt, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), cont, None))
     ck = np.zeros(L.smo_kdyn_checkpoint_bytes(h, nit, every) // 16, dtype=complex)
-    seg = np.zeros(L.smo_kdyn_snapshot_bytes(h, every) // 16, dtype=complex)
+    seg = np.zeros(L.smo_kdyn_segment_bytes(h, every) // 16, dtype=complex)
     emul.check(L.smo_kdyn_forward_ckpt(h, emul.ptr(B0), emul.ptr(U), Rm, dt, nit, every, emul.ptr(ck), C.byref(Jc), 0, None))
     gBc, gUc = np.zeros(3 * gsz), np.zeros(3 * gsz)
     emul.check(L.smo_kdyn_adjoint_ckpt(h, Rm, dt, nit, every, emul.ptr(ck), emul.ptr(seg), emul.ptr(gBc), emul.ptr(gUc), cont, None))

@@ -35,8 +35,6 @@ import os
 chunk_sets = [tuple(int(v) for v in cs.split(",")) for cs in os.environ.get("CHUNKS", "1,1").split(";")]
 if os.environ.get("GRAPH"):
     lib.smo_kdyn_use_graph(dom.h, 1)
-if os.environ.get("FUSED_Z") is not None:
-    lib.smo_kdyn_set_option(dom.h, 1, int(os.environ["FUSED_Z"]))
 for _ in range(3):
     kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)   # warm-up (lazy module loading, graph capture)
 for cf, ca in chunk_sets:
