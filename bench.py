@@ -41,8 +41,9 @@ WORKLOADS = {
     "sh23ens": (256, None, 0.1, 500),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-# (profiles/r1f_kdyn128_adj_step_ncu.txt: 396.4 MB read + 177.9 MB written; algorithmic 566.2 MB)
-NCU_TRAFFIC = {("kdyn128", 1): 574.3e6}
+# (profiles/r1g_kdyn128_adj_step_ncu.txt: 509.6 MB read + 185.4 MB written - it also reads the forward state from its
+# snapshot slot and read-modify-writes the running sum of the gradient integrand; algorithmic model 566.2 MB)
+NCU_TRAFFIC = {("kdyn128", 1): 695.0e6}
 METRIC = "Grad_f evals/s (fwd+adjoint)"
 UNIT = "Grad_f evals/s"
 
