@@ -126,6 +126,59 @@ def test_kdyn_checkpointed_sweep(every, adj):
     assert abs(fc - fo) <= TOL * abs(fo) and relerr(gc[0], go[0]) <= TOL and relerr(gc[1], go[1]) <= TOL
 
 
+def _taylor_slopes(f, grad, ip, X, dX, eps0=1e-3, n=5):
+    """second-order Taylor-remainder test (what the reference's Adjoint_Gradient_Test checks, TG:47-150, restated):
+    R2(eps) = |f(X + eps dX) - f(X) - eps <Grad_f(X), dX>| must decay like eps^2"""
+    f0 = f(X)
+    g = grad(X)
+    dfd = sum(ip(gi, di) for gi, di in zip(g, dX))
+    eps = [eps0 / 2 ** k for k in range(n)]
+    R2 = [abs(f([x + e * d for x, d in zip(X, dX)]) - f0 - e * dfd) for e in eps]
+    return [np.log(R2[k] / R2[k + 1]) / np.log(2.0) for k in range(n - 1)], R2
+
+
+def test_taylor_remainder_sh23_config1():
+    """BASELINE config 1 at full size (Npts=256, T=50, dt=0.1): slope 2 of the Taylor remainder with the CUDA callables"""
+    from spheremanopt_b200 import sh23
+    dom, X0 = sh23.Generate_IC(0.0725)
+    nit = 500
+    store = sh23.GEN_BUFFER(dom, nit)
+    args = (dom, 0.1, nit, nit, store)
+    dX = np.random.RandomState(5).standard_normal(X0.size) * np.sqrt(0.0725)
+    slopes, R2 = _taylor_slopes(lambda X: sh23.FWD_Solve_IVP_Lin(X, *args), lambda X: sh23.ADJ_Solve_IVP_Lin(X, *args),
+                                lambda a, b: sh23.Inner_Prod(a, b, dom), [X0], [dX])
+    assert all(abs(s - 2.0) < 0.1 for s in slopes), (slopes, R2)
+
+
+def test_taylor_remainder_kdyn_config3_grid():
+    """BASELINE config 3 grid (128^3, Rm=10, dt=1e-3; 20 steps), device-resident vectors, B and U perturbed together"""
+    import torch
+    from spheremanopt_b200 import kdyn
+    from spheremanopt_b200.devvec import DevVec
+    Npts, nit = 128, 20
+    dom = kdyn.Domain(Npts)
+    M = dom.M
+
+    def field(seed):      # band-limited solenoidal field through the library's own transforms
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        v = torch.randn(3 * M ** 3, dtype=torch.float64, generator=g).to(dom.device)
+        c = kdyn.to_coef(dom, v)
+        kx, ky, kz = kdyn._wavenumbers(dom)
+        k2 = kx * kx + ky * ky + kz * kz
+        c = c * torch.exp(-0.2 * torch.sqrt(k2))
+        kd = (kx * c[0] + ky * c[1] + kz * c[2]) / torch.where(k2 == 0, torch.ones_like(k2), k2)
+        c = torch.stack([c[0] - kx * kd, c[1] - ky * kd, c[2] - kz * kd]) * (k2 != 0)
+        v = kdyn.to_grid(dom, c)
+        return DevVec(v / np.sqrt(kdyn.Inner_Prod_3(DevVec(v), DevVec(v), dom)))
+    X = [field(1), field(2)]
+    dX = [field(3), field(4)]
+    store = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=0)
+    args = (dom, 10.0, 1e-3, nit, nit, store)
+    slopes, R2 = _taylor_slopes(lambda Y: kdyn.FWD_Solve_IVP_Lin(Y, *args), lambda Y: kdyn.ADJ_Solve_IVP_Lin(Y, *args),
+                                lambda a, b: kdyn.Inner_Prod_3(a, b, dom), X, dX, eps0=1e-2)
+    assert all(abs(s - 2.0) < 0.1 for s in slopes), (slopes, R2)
+
+
 def test_kdyn_graph_replay():
     """CUDA-graph replay of the time loops (eager first call, capture on the second, replay afterwards) changes nothing"""
     from spheremanopt_b200 import kdyn
