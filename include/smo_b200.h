@@ -32,7 +32,7 @@ long long smo_launch_count(void);
 
 /* flags */
 #define SMO_ADJOINT_CONTINUOUS 1 /* Adjoint_type="Continuous" (SH:654-656, KD:904-910) */
-#define SMO_COST_INTEGRATED 2    /* Cost_function="Integrated" (KD:655-669); not implemented yet: returns an error */
+#define SMO_COST_INTEGRATED 2    /* Cost_function="Integrated" (KD:655-669, 738-742, 861-864): J = dt * sum_n <B^n,B^n> */
 
 /* ------------------------------------------------------------------------------------------------------------
  * Swift-Hohenberg SH23 (1-D periodic Fourier, SBDF1, dealias 2)

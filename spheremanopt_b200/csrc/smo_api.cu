@@ -101,6 +101,7 @@ static int rt_copy2d(void* d, size_t dp, const void* s, size_t sp, size_t w, siz
 static int rt_memset(void* d, int v, size_t n, rt_stream) { memset(d, v, n); return 0; }
 static int rt_sync(rt_stream) { return 0; }
 static int rt_check(const char*) { return 0; }
+template <class K> static int grid_for(int nwork) { return nwork < 3 ? nwork : 3; }
 template <class K> static int launch(const typename K::Params& p, rt_stream) {
   if (p.nwork <= 0) return 0;
   const int grid = p.nwork < 3 ? p.nwork : 3;   // > 1 work item per CTA exercises the persistent loop
@@ -150,17 +151,20 @@ template <class K> struct LaunchCfg {
     return v;
   }
 };
-template <class K> static int launch(const typename K::Params& p, rt_stream st) {
-  if (p.nwork <= 0) return 0;
+// persistent-style grid: at most one resident wave (a multiple of the SM count), CTAs loop over work items
+template <class K> static int grid_for(int nwork) {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  // persistent-style grid: at most one resident wave (a multiple of the SM count), CTAs loop over work items
   const long long cap = (long long)g_num_sms * LaunchCfg<K>::blocks_per_sm();
-  const int grid = (int)(p.nwork < cap ? p.nwork : cap);
+  return (int)(nwork < cap ? nwork : cap);
+}
+template <class K> static int launch(const typename K::Params& p, rt_stream st) {
+  if (p.nwork <= 0) return 0;
+  const int grid = grid_for<K>(p.nwork);
   smo_kernel<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
   g_launches++;
   return rt_check("kernel launch");
@@ -424,6 +428,7 @@ struct smo_kdyn {
   cplx* p2[MAXF];    // [Nh][M][nz]
   cplx* cw[MAXF];    // coefficient work
   cplx* G[3]; cplx* NU[3]; cplx* W[3];
+  double* jparts; size_t jparts_cap; size_t jparts_used;   // cost "Integrated": per-CTA partial sums of |B^n|^2 of every x pass
   cplx* acc[3];      // [Nh][M][nz] running sum over the adjoint steps of the x-spectra of (curl G) x B_f (allocated on first use)
   double* Ug[3];     // projected velocity on the grid [M][M][nz]
   double* Ut;        // the same, tile-major [M*nz/4][3][M][4] (read by the fused x passes)
@@ -730,22 +735,30 @@ template <int M> struct KdOps {
     }
   }
   // forward: x-spectra of B (the snapshot slot or the work arrays) in, x-spectra of U x B out (work arrays)
-  static int x_fwd(smo_kdyn* h, cplx* const* bp2, rt_stream st, int z0 = 0, int nzc = -1) {
+  static int x_fwd(smo_kdyn* h, cplx* const* bp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
     XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = bp2[f]; p.sout[f] = h->p2[f]; }
     prof_begin(h, PK_X, st);
-    int rc = launch<XFused<F, X_FWD>>(p, st);
+    int rc;
+    if (integ) {   // cost "Integrated": this launch's per-CTA sums of |B|^2 go to the next free slots of jparts
+      const int grid = grid_for<XFused<F, X_FWD, true>>(p.nwork);
+      if (h->jparts_used + (size_t)grid > h->jparts_cap) return fail(SMO_E_STATE, "x_fwd: partial-sum buffer too small");
+      p.jpart = h->jparts + h->jparts_used; h->jparts_used += (size_t)grid;
+      rc = launch<XFused<F, X_FWD, true>>(p, st);
+    } else {
+      rc = launch<XFused<F, X_FWD>>(p, st);
+    }
     prof_end(h, PK_X, st);
     return rc;
   }
   // adjoint: x-spectra of curl G (work arrays) and of the forward state B_f (read straight from its snapshot slot) in
-  static int x_adj(smo_kdyn* h, cplx* const* bfp2, rt_stream st, int z0 = 0, int nzc = -1) {
+  static int x_adj(smo_kdyn* h, cplx* const* bfp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
     XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = h->p2[f]; p.sout[f] = h->p2[f]; p.sin[3 + f] = bfp2[f]; }
     for (int c = 0; c < 3; ++c) p.sout[3 + c] = h->acc[c];    // (curl G) x B_f: summed over the sweep on the x-spectra
     p.accumulate = 1;
     prof_begin(h, PK_XA, st);
-    int rc = launch<XFused<F, X_ADJ>>(p, st);
+    int rc = integ ? launch<XFused<F, X_ADJ, true>>(p, st) : launch<XFused<F, X_ADJ>>(p, st);
     prof_end(h, PK_XA, st);
     return rc;
   }
@@ -810,14 +823,14 @@ template <int M> struct KdOps {
   // y -> fused x -> y part of a step: p1t (z-slab side) -> p1t.  xs = x-spectra of the forward state: WRITTEN by the inverse
   // y pass of a forward step (the snapshot slot of state n, or the work arrays), READ by the x pass of an adjoint step.
   // (with in-kernel hand-shakes the first y pass waits for "p1t filled", the last one signals "p1 filled")
-  static int yxy(smo_kdyn* h, int mode, cplx* const* xs, rt_stream st) {
+  static int yxy(smo_kdyn* h, int mode, cplx* const* xs, rt_stream st, bool integ = false) {
     const int nch = pick_chunks(h, mode == 0 ? h->chunks_fwd : h->chunks_adj, mode == 0 ? 3 : 6, TY > 4 ? TY : 4);
     const int nzc = h->nz / nch;
     for (int ch = 0; ch < nch; ++ch) {
       const int z0 = ch * nzc, zc = nch > 1 ? nzc : -1;
       TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, st, z0, zc, ch == 0 ? XS_B : XS_NONE));
-      if (mode == 0) TRY(x_fwd(h, xs, st, z0, zc));
-      else TRY(x_adj(h, xs, st, z0, zc));
+      if (mode == 0) TRY(x_fwd(h, xs, st, z0, zc, integ));
+      else TRY(x_adj(h, xs, st, z0, zc, integ));
       TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, zc, ch == nch - 1 ? XS_A : XS_NONE));
     }
     return 0;
@@ -961,14 +974,15 @@ struct FwdStep { cplx* cin[3]; cplx* cout[3]; cplx* xs[3]; };
 // (snapshot slot) -> [fused x] -> [y forward] -> p1 -> [fused z step: coefficients of step n+1 written, and already on their
 // way back to p1].  tail_xs_only: the last "step" only produces the x-spectra of its state (snapshot of the final state).
 template <int M, class StepFn>
-static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double Rm, double dt, StepFn step, rt_stream st) {
+static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double Rm, double dt, StepFn step, rt_stream st,
+                           bool integ = false) {
   if (n_steps <= 0) return 0;
   // multi-GPU: the transposes are remote stores / loads of the kernels themselves; their hand-shakes are either fused into
   // the kernels (ks: producer signals at its end, consumer waits at its start) or separate barrier launches (a2a)
   const bool ks = kernel_sync(h);
   if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));     // every rank has left whatever used the pencil buffers before
   const FwdStep first = step(0), last = step(n_steps - 1);
-  GraphKey key; key.kind = tail_xs_only ? 3 : 1; key.n = n_steps; key.opts = graph_opts(h); key.p0 = first.xs[0]; key.p1 = last.cout[0];
+  GraphKey key; key.kind = (tail_xs_only ? 3 : 1) + (integ ? 10 : 0); key.n = n_steps; key.opts = graph_opts(h); key.p0 = first.xs[0]; key.p1 = last.cout[0];
   key.p2 = first.cin[0]; key.Rm = Rm; key.dt = dt;    // (everything else a step touches follows from these by construction)
   return run_graphed(h, key, st, [&](rt_stream s) -> int {
     TRY(KdOps<M>::inv_z(h, first.cin, h->p1, 3, s, XS_B));
@@ -976,7 +990,7 @@ static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double R
     for (int n = 0; n < n_steps; ++n) {
       const FwdStep b = step(n);
       if (tail_xs_only && n == n_steps - 1) return KdOps<M>::y_only(h, b.xs, s);
-      TRY(KdOps<M>::yxy(h, 0, b.xs, s));
+      TRY(KdOps<M>::yxy(h, 0, b.xs, s, integ));
       if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, s));
       const bool more = n + 1 < n_steps;
       TRY(KdOps<M>::zstep(h, 0, b.cin, b.cout, more, Rm, dt, s));
@@ -989,13 +1003,44 @@ static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double R
 static void pingpong(cplx* const* a, cplx* const* b, int n, FwdStep& f) {
   for (int c = 0; c < 3; ++c) { f.cin[c] = (n & 1) ? b[c] : a[c]; f.cout[c] = (n & 1) ? a[c] : b[c]; }
 }
+// cost "Integrated" (KD:655-669): J = dt * sum_{n=0}^{N} <B^n,B^n>.  The states 0..N-1 pass through the forward x pass, which
+// sums |B^n|^2 over its grid points into per-CTA partials (deterministic: fixed tile assignment, fixed-order sums); the final
+// state is added from its grid values.
+static int jparts_begin(smo_kdyn* h, int n_steps, rt_stream st) {
+  const size_t per_step = 4096;     // >= CTAs of one step's x passes (<= 8 resident CTAs/SM x SMs, all chunks)
+  const size_t need = (size_t)n_steps * per_step;
+  if (need > h->jparts_cap) {
+    rt_free(h->jparts); h->jparts = nullptr; h->jparts_cap = 0;
+#if !defined(SMO_EMUL)
+    if (h->graphs) { for (GraphEntry& e : h->graphs->e) if (e.exec) cudaGraphExecDestroy(e.exec); h->graphs->e.clear(); }
+#endif
+    TRY(rt_malloc((void**)&h->jparts, sizeof(double) * need));
+    h->jparts_cap = need;
+  }
+  h->jparts_used = 0;
+  return rt_memset(h->jparts, 0, sizeof(double) * h->jparts_cap, st);
+}
+// *J_host = J_final_term_host * dt + dt * scale * sum(partials)
+static int jparts_finish(smo_kdyn* h, size_t used, double dt, double scale, double* J_host, rt_stream st) {
+  SumParams sp;
+  sp.partials = h->jparts; sp.out = h->vwork; sp.nwork = 1; sp.nsteps = 1; sp.npart = (int)used; sp.nq = 1; sp.a = dt * scale;
+  TRY(launch<FinalSum>(sp, st));
+  double part = 0.0;
+  TRY(rt_d2h(&part, h->vwork, sizeof(double), st));
+  TRY(rt_sync(st));
+  *J_host = dt * (*J_host) + part;
+  return 0;
+}
 template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
-                                       void* snaps, double* J_host, rt_stream st) {
+                                       void* snaps, double* J_host, int flags, rt_stream st) {
+  const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   TRY(kd_set_U<M>(h, U, st));
+  if (integ) TRY(jparts_begin(h, n_iters, st));
   TRY(KdOps<M>::to_coef(h, B0, h->G, st));
   auto step = [&](int n) { FwdStep f; pingpong(h->G, h->NU, n, f); snap_xs(h, snaps, n, f.xs); return f; };
   // n_iters steps + the x-spectra of the final state (slot n_iters: continuous adjoint, and the cost below)
-  TRY((kd_forward_loop<M>(h, n_iters + 1, true, Rm, dt, step, st)));
+  TRY((kd_forward_loop<M>(h, n_iters + 1, true, Rm, dt, step, st, integ)));
+  const size_t jused = h->jparts_used;   // (a graph replay does not advance the host-side counter: recompute it below)
   const FwdStep fin = step(n_iters);
   cplx* sf[3];
   snap_final(h, snaps, n_iters, sf);
@@ -1005,7 +1050,9 @@ template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const doub
   TRY(KdOps<M>::x_c2r(h, fin.xs, g, st));
   const double scale = 1.0 / ((double)M * M * M);
   prof_collect(h, st);
-  return smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st);
+  TRY(smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st));
+  (void)jused;
+  return integ ? jparts_finish(h, h->jparts_cap, dt, scale, J_host, st) : 0;
 }
 template <int M> static int kd_prep(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                                     double* out, rt_stream st) {
@@ -1021,17 +1068,17 @@ template <int M> static int kd_prep(smo_kdyn* h, const double* B0, const double*
 // persist between calls, so a checkpointed sweep can call this once per recomputed segment.  3 transforms in, 3 out.
 struct XsPtr { cplx* p[3]; };
 template <int M, class StateFn>
-static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn state, rt_stream st) {
+static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn state, rt_stream st, bool integ = false) {
   if (count <= 0) return 0;
   const bool ks = kernel_sync(h);
   if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));
-  GraphKey key; key.kind = 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0).p[0]; key.p1 = state(count - 1).p[0]; key.p2 = nullptr; key.Rm = Rm; key.dt = dt;
+  GraphKey key; key.kind = integ ? 12 : 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0).p[0]; key.p1 = state(count - 1).p[0]; key.p2 = nullptr; key.Rm = Rm; key.dt = dt;
   return run_graphed(h, key, st, [&](rt_stream q) -> int {
     TRY(KdOps<M>::inv_z(h, h->W, h->p1, 3, q, XS_B));
     if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, q));
     for (int i = 0; i < count; ++i) {
       const XsPtr bf = state(i);
-      TRY(KdOps<M>::yxy(h, 1, bf.p, q));
+      TRY(KdOps<M>::yxy(h, 1, bf.p, q, integ));
       if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, q));
       const bool more = i + 1 < count;
       TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more, Rm, dt, q));
@@ -1051,14 +1098,15 @@ template <int M> static int kd_adjoint_finish(smo_kdyn* h, double Rm, double dt,
 template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_iters, const void* snapsc, double* gB,
                                        double* gU, int flags, rt_stream st) {
   const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
+  const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   void* snaps = const_cast<void*>(snapsc);
   cplx* s[3];
   snap_final(h, snaps, n_iters, s);
-  TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
+  TRY(KdOps<M>::compat(h, s, Rm, dt, cont | (integ ? 1 : 0), st));
   TRY(KdOps<M>::acc_begin(h, st));
   // adjoint step m linearises about snapshot idx(m): snapshot_index -1-m (continuous) / -2-m (discrete)
   auto state = [&](int m) { XsPtr x; snap_xs(h, snaps, cont ? (n_iters - m) : (n_iters - 1 - m), x.p); return x; };
-  TRY((kd_adjoint_loop<M>(h, n_iters, Rm, dt, state, st)));
+  TRY((kd_adjoint_loop<M>(h, n_iters, Rm, dt, state, st, integ)));
   return kd_adjoint_finish<M>(h, Rm, dt, cont, gB, gU, st);
 }
 
@@ -1075,8 +1123,10 @@ static void ckpt_coef(smo_kdyn* h, void* ck, int n, int n_iters, int every, cplx
   for (int c = 0; c < 3; ++c) out[c] = (n & 1) ? h->NU[c] : h->G[c];
 }
 template <int M> static int kd_forward_ckpt(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
-                                            int every, void* ck, double* J_host, rt_stream st) {
+                                            int every, void* ck, double* J_host, int flags, rt_stream st) {
+  const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   TRY(kd_set_U<M>(h, U, st));
+  if (integ) TRY(jparts_begin(h, n_iters, st));
   cplx* s0[3];
   snap_ptrs(h, ck, 0, s0);
   TRY(KdOps<M>::to_coef(h, B0, s0, st));
@@ -1085,20 +1135,22 @@ template <int M> static int kd_forward_ckpt(smo_kdyn* h, const double* B0, const
     for (int c = 0; c < 3; ++c) f.xs[c] = h->p2[c];
     return f;
   };
-  TRY((kd_forward_loop<M>(h, n_iters, false, Rm, dt, step, st)));
+  TRY((kd_forward_loop<M>(h, n_iters, false, Rm, dt, step, st, integ)));
   snap_ptrs(h, ck, ckpt_slot_of(n_iters, n_iters, every), s0);
   TRY(KdOps<M>::to_grid(h, s0, h->gwork, st));
   const double scale = 1.0 / ((double)M * M * M);
   prof_collect(h, st);
-  return smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st);
+  TRY(smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st));
+  return integ ? jparts_finish(h, h->jparts_cap, dt, scale, J_host, st) : 0;
 }
 template <int M> static int kd_adjoint_ckpt(smo_kdyn* h, double Rm, double dt, int n_iters, int every, const void* ckc, void* seg,
                                             double* gB, double* gU, int flags, rt_stream st) {
   const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
+  const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   void* ck = const_cast<void*>(ckc);
   cplx* s[3];
   snap_ptrs(h, ck, ckpt_slot_of(n_iters, n_iters, every), s);
-  TRY(KdOps<M>::compat(h, s, Rm, dt, cont, st));
+  TRY(KdOps<M>::compat(h, s, Rm, dt, cont | (integ ? 1 : 0), st));
   TRY(KdOps<M>::acc_begin(h, st));
   const int nseg = (n_iters + every - 1) / every;
   for (int k = nseg - 1; k >= 0; --k) {
@@ -1120,7 +1172,7 @@ template <int M> static int kd_adjoint_ckpt(smo_kdyn* h, double Rm, double dt, i
     TRY((kd_forward_loop<M>(h, last + 1, true, Rm, dt, step, st)));
     if (k != nseg - 1) TRY(KdOps<M>::curl_G(h, Rm, dt, st));   // W = curl G (the fused step keeps it on chip only)
     auto sweep = [&](int i) { XsPtr x; snap_xs(h, seg, last - i, x.p); return x; };
-    TRY((kd_adjoint_loop<M>(h, n1 - n0, Rm, dt, sweep, st)));
+    TRY((kd_adjoint_loop<M>(h, n1 - n0, Rm, dt, sweep, st, integ)));
   }
   return kd_adjoint_finish<M>(h, Rm, dt, cont, gB, gU, st);
 }
@@ -1170,6 +1222,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->comm = comm;
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
+  h->jparts = nullptr; h->jparts_cap = 0; h->jparts_used = 0;
   h->graphs = nullptr; h->capturing = 0; h->cap_a0 = h->cap_b0 = 0; h->epoch_dev = nullptr;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
   h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0;
@@ -1216,7 +1269,7 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
     rt_free(h->p1[f]); rt_free(h->p2[f]); rt_free(h->cw[f]);
   }
   for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); rt_free(h->acc[c]); }
-  rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut);
+  rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut); rt_free(h->jparts);
 #if !defined(SMO_EMUL)
   if (h->peer_on) {
     for (int s = 0; s < h->nranks; ++s) {
@@ -1250,7 +1303,7 @@ extern "C" size_t smo_kdyn_segment_bytes(const smo_kdyn_t* h, int every) {
 static int kd_args(smo_kdyn* h, double Rm, double dt, int n_iters, int flags, const char* who) {
   if (!h) return fail(SMO_E_ARG, "%s: null handle", who);
   if (!(Rm > 0) || !(dt > 0) || n_iters < 0) return fail(SMO_E_ARG, "%s: bad Rm/dt/n_iters", who);
-  if (flags & SMO_COST_INTEGRATED) return fail(SMO_E_UNSUPPORTED, "%s: Cost_function=\"Integrated\" is not implemented", who);
+  (void)flags;
   return 0;
 }
 extern "C" int smo_kdyn_forward(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
@@ -1258,7 +1311,7 @@ extern "C" int smo_kdyn_forward(smo_kdyn_t* h, const double* B0, const double* U
   TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward"));
   if (!B0 || !U || !snaps || !J_host) return fail(SMO_E_ARG, "smo_kdyn_forward: null buffer");
   rt_stream st = (rt_stream)stream;
-  KD_DISPATCH(h, kd_forward, h, B0, U, Rm, dt, n_iters, snaps, J_host, st)
+  KD_DISPATCH(h, kd_forward, h, B0, U, Rm, dt, n_iters, snaps, J_host, flags, st)
 }
 extern "C" int smo_kdyn_prep(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                              double* out, void* stream) {
@@ -1283,7 +1336,7 @@ extern "C" int smo_kdyn_forward_ckpt(smo_kdyn_t* h, const double* B0, const doub
   TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward_ckpt"));
   if (!B0 || !U || !ckpt || !J_host || every < 1) return fail(SMO_E_ARG, "smo_kdyn_forward_ckpt: bad argument");
   rt_stream st = (rt_stream)stream;
-  KD_DISPATCH(h, kd_forward_ckpt, h, B0, U, Rm, dt, n_iters, every, ckpt, J_host, st)
+  KD_DISPATCH(h, kd_forward_ckpt, h, B0, U, Rm, dt, n_iters, every, ckpt, J_host, flags, st)
 }
 extern "C" int smo_kdyn_adjoint_ckpt(smo_kdyn_t* h, double Rm, double dt, int n_iters, int every, const void* ckpt, void* seg,
                                      double* gB, double* gU, int flags, void* stream) {

@@ -128,6 +128,9 @@ SMO_HD int imin(int a, int b) { return a < b ? a : b; }
 template <class K, class = void> struct is_v2 { static constexpr bool value = false; };
 template <class K> struct is_v2<K, decltype((void)K::V2)> { static constexpr bool value = K::V2; };
 
+template <class K, class = void> struct has_finish { static constexpr bool value = false; };
+template <class K> struct has_finish<K, decltype((void)K::HAS_FINISH)> { static constexpr bool value = K::HAS_FINISH; };
+
 template <class K, class = void> struct has_sync_kinds { static constexpr bool value = false; };
 template <class K> struct has_sync_kinds<K, decltype((void)K::sync_after(0))> { static constexpr bool value = true; };
 
@@ -180,6 +183,13 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
   for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
     for (int step = 0; step < p.nsteps; ++step)
       PhaseStep<K, 0, false>::run(p, work, step, (int)threadIdx.x, smo_smem, st);
+  }
+  if constexpr (has_finish<K>::value) {   // per-CTA epilogue after the last work item (e.g. deterministic partial sums)
+    __syncthreads();
+    Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
+    K::template finish<0>(p, c, st);
+    __syncthreads();
+    K::template finish<1>(p, c, st);
   }
   if constexpr (has_xsync<K>::value) {
     if (p.xs.sig_n > 0) {
@@ -234,6 +244,10 @@ template <class K> void emul_kernel(int grid, size_t smem_bytes, const typename 
     }
     for (int work = cta; work < p.nwork; work += grid)
       for (int step = 0; step < p.nsteps; ++step) EmulStep<K, 0, false>::run(p, work, step, sm, st);
+    if constexpr (has_finish<K>::value) {
+      for (int tid = 0; tid < K::THREADS; ++tid) { Ctx c; c.cta = cta; c.ncta = grid; c.tid = tid; c.smem = sm; K::template finish<0>(p, c, st[tid]); }
+      for (int tid = 0; tid < K::THREADS; ++tid) { Ctx c; c.cta = cta; c.ncta = grid; c.tid = tid; c.smem = sm; K::template finish<1>(p, c, st[tid]); }
+    }
   }
 }
 #endif

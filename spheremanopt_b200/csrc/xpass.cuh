@@ -230,9 +230,12 @@ struct XFParams {
   double scale;
   const cplx* tw;
   int accumulate;            // X_ADJ: outputs 3..5 (x-spectra of (curl G) x B_f) are ADDED to sout[3..5] instead of stored
+  double* jpart;             // INTEG forward: [gridDim] per-CTA sums of |B|^2 over the grid points this launch visited
 };
 
-template <class F, int MODE> struct XFused {
+// INTEG = Cost_function "Integrated" (KD:655-669, 861-864): the forward pass also sums |B^n|^2 over its grid points
+// (deterministic per-CTA partials), the adjoint pass adds the source -2 B_f to the (curl G) x U products.
+template <class F, int MODE, bool INTEG = false> struct XFused {
   typedef XFParams Params;
   typedef typename F::Swapped FS;
   static constexpr bool V2 = true;
@@ -269,8 +272,20 @@ template <class F, int MODE> struct XFused {
   struct State {
     double re[RT], im[RT];
     double wr, wi;     // w_M^jj = exp(-2 pi i jj / M): base of this thread's inter-stage twiddles (wide mapping)
+    double jacc;       // INTEG forward: running sum of this thread's |B|^2
     int it;
   };
+  static constexpr bool HAS_FINISH = INTEG && MODE == X_FWD;
+  // fixed-order sum of the threads' partial sums -> jpart[cta]
+  template <int STEP> SMO_HD static void finish(const Params& p, const Ctx& c, State& st) {
+    double* R = reinterpret_cast<double*>(x_buf(c.smem));
+    if (STEP == 0) { R[c.tid] = st.jacc; return; }
+    if (c.tid == 0) {
+      double s = 0.0;
+      for (int t = 0; t < THREADS; ++t) s += R[t];
+      p.jpart[c.cta] = s;
+    }
+  }
 
   SMO_HD static cplx* sin_buf(unsigned char* s) { return reinterpret_cast<cplx*>(s); }
   SMO_HD static cplx* su_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
@@ -322,6 +337,7 @@ template <class F, int MODE> struct XFused {
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
     const cplx w = ldg_c(p.tw + (c.tid % FT) % RT);
     st.wr = w.x; st.wi = w.y;
+    st.jacc = 0.0;
     st.it = 0;
   }
 
@@ -399,6 +415,7 @@ template <class F, int MODE> struct XFused {
           const cplx b1 = Xa[c1 * HP * XLP + R1 * i];
           e0 = u1.x * ox - u2.x * b1.x;
           e1 = u1.y * oy - u2.y * b1.y;
+          if (INTEG) st.jacc += ox * ox + oy * oy;
         } else if (f < 3) {
           // (W x U)_c = W_c1 U_c2 - W_c2 U_c1 with c1 = f (own), c = f+2, c2 = f+1
           const int c2 = (f + 1) % 3;
@@ -406,6 +423,10 @@ template <class F, int MODE> struct XFused {
           const cplx w2 = Xa[c2 * HP * XLP + R1 * i];
           e0 = ox * u2.x - w2.x * u1.x;
           e1 = oy * u2.y - w2.y * u1.y;
+          if (INTEG) {   // source -2 B_f of the G equation (KD:862-864), component c = f+2
+            const cplx bc = Xa[(3 + (f + 2) % 3) * HP * XLP + R1 * i];
+            e0 -= 2.0 * bc.x; e1 -= 2.0 * bc.y;
+          }
         } else {
           // (W x B)_c = W_c1 B_c2 - W_c2 B_c1 with c2 = f-3 (own), c = c2+1, c1 = c2+2
           const int g = f - 3, c1 = (g + 2) % 3;

@@ -116,6 +116,37 @@ def test_kdyn_checkpointed_emulated(L, every, cont):
     L.smo_kdyn_destroy(h)
 
 
+@pytest.mark.parametrize("adj,every", [(0, 0), (1, 0), (0, 3)])
+def test_kdyn_integrated_cost_emulated(L, adj, every):
+    """Cost_function="Integrated" (KD:655-669, 738-742, 861-864): J = dt sum_n <B^n,B^n>, adjoint source -2 B_f"""
+    Npts, nit = 16, 5
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    emul.check(L.smo_kdyn_create(C.byref(h), Npts, od.L, 0, 1, None))
+    gsz = L.smo_kdyn_grid_elems(h)
+    Rm, dt = 2.0, 1e-3
+    J = C.c_double()
+    gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
+    flags = 2 | adj      # SMO_COST_INTEGRATED | SMO_ADJOINT_CONTINUOUS
+    if every:
+        ck = np.zeros(L.smo_kdyn_checkpoint_bytes(h, nit, every) // 16, dtype=complex)
+        seg = np.zeros(L.smo_kdyn_segment_bytes(h, every) // 16, dtype=complex)
+        emul.check(L.smo_kdyn_forward_ckpt(h, emul.ptr(B0), emul.ptr(U), Rm, dt, nit, every, emul.ptr(ck), C.byref(J), flags, None))
+        emul.check(L.smo_kdyn_adjoint_ckpt(h, Rm, dt, nit, every, emul.ptr(ck), emul.ptr(seg), emul.ptr(gB), emul.ptr(gU), flags, None))
+    else:
+        snaps = np.zeros(L.smo_kdyn_snapshot_bytes(h, nit) // 16, dtype=complex)
+        emul.check(L.smo_kdyn_forward(h, emul.ptr(B0), emul.ptr(U), Rm, dt, nit, emul.ptr(snaps), C.byref(J), flags, None))
+        emul.check(L.smo_kdyn_adjoint(h, Rm, dt, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), flags, None))
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    at = "Continuous" if adj else "Discrete"
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D, "Integrated", at)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D, "Integrated", at)
+    assert abs(-J.value - fo) <= TOL * abs(fo)
+    assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    L.smo_kdyn_destroy(h)
+
+
 def test_vector_kernels_emulated(L):
     od = okd.domain_kdyn(16)
     n = 3 * od.M ** 3

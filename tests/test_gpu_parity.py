@@ -203,6 +203,24 @@ def test_kdyn_graph_replay():
         assert fc == f0 and np.array_equal(gc[0], g0[0]) and np.array_equal(gc[1], g0[1])
 
 
+@pytest.mark.parametrize("Npts,nit,adj,every", [(24, 12, "Discrete", 0), (32, 6, "Continuous", 0), (24, 12, "Discrete", 5)])
+def test_kdyn_integrated_cost(Npts, nit, adj, every):
+    """Cost_function="Integrated" (KD:655-669, 738-742, 861-864), stored and checkpointed sweeps"""
+    from spheremanopt_b200 import kdyn
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    Rm, dt = 1.0, 1e-3
+    store = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=every)
+    f = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, store, "Integrated", adj)
+    g = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, Rm, dt, nit, nit, store, "Integrated", adj)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D, "Integrated", adj)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D, "Integrated", adj)
+    assert abs(f - fo) <= TOL * abs(fo)
+    assert relerr(g[0], go[0]) <= TOL and relerr(g[1], go[1]) <= TOL
+
+
 def test_kdyn_non_solenoidal_input():
     """adversarial input (not band-limited, not divergence free, non-zero mean): exercises the truncation on first
     gather, the projection of the parameter field U [D2-8] and the k.B carry of the closed-form CNAB1 pencil"""
