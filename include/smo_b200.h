@@ -120,7 +120,8 @@ int smo_kdyn_prep_host(smo_kdyn_t* h, const double* B0_host, const double* U_hos
 /* transform helpers (tests, initial conditions): grid [3][grid_elems] <-> coefficients [3][coef_elems] */
 int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid_dev, void* coef_dev, void* stream);
 int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef_dev, double* grid_dev, void* stream);
-/* per-kernel timing of the time loops: which = 0 off, 1..6 = z-pass, y-pass, fused forward x-pass, epilogue, all-to-all, fused adjoint x-pass.
+/* per-kernel timing of the time loops: which = 0 off, 1 = z passes outside the fused step, 2 = y passes, 3 = fused forward x pass,
+ * 5 = all-to-all / barrier launches, 6 = fused adjoint x pass, 7 = fused z step.
  * smo_kdyn_profile_read returns the accumulated CUDA-event time (ms) and launch count since the last set. */
 int smo_kdyn_profile_set(smo_kdyn_t* h, int which);
 int smo_kdyn_profile_read(smo_kdyn_t* h, double* total_ms, long long* launches);

@@ -84,17 +84,14 @@ SMO_HD C3 axpy3(double s, const C3& x, const C3& y) {   // s*x + y
   return o;
 }
 
-enum { EPI_FWD = 0, EPI_ADJ = 1, EPI_COMPAT = 2, EPI_FINAL = 3, EPI_CURL = 4, EPI_NUFIN = 5 };
+enum { EPI_COMPAT = 2, EPI_FINAL = 3, EPI_CURL = 4, EPI_NUFIN = 5 };
 
-// EPI_FWD   : a[0..2] = to_coef(U x B) (EMF), b[0..2] = B^n            -> o[0..2] = B^{n+1}
-// EPI_ADJ   : a[0..2] = to_coef(W x U), a[3..5] = to_coef(W x B_f), b[0..2] = G, b[3..5] = nu
-//             -> o[0..2] = G', o[3..5] = nu', o2[0..2] = i k x G'   (flag&1: "Integrated" cost, o2[3..5] = B_f coeffs)
+// (the per-step updates - CNAB1 step of B, adjoint step of G - live in the fused z step, zstep.cuh, and use the helpers above)
 // EPI_COMPAT: b[0..2] = B^N -> o[0..2] = G^0, o2[0..2] = i k x G^0   (flag&1 Integrated, flag&2 Continuous)
 // EPI_FINAL : b[0..2] = G^N -> o[0..2] = dt*alpha*G^N  (flag&2 Continuous: plain copy)
 // EPI_CURL  : b[0..2] = G   -> o2[0..2] = i k x G        (segment boundaries of a checkpointed adjoint sweep)
 // EPI_NUFIN : b[0..2] = to_coef(sum_m (curl G^m) x B_f^m) -> o[0..2] = nu^N = -dt P_k[b]   (KD:874-877 summed over the sweep:
 //             nu' = nu + dt P_k[-H] with nu^0 = 0 is linear in H, so the sum is taken before the transforms, see xpass.cuh)
-// EPI_ADJ flag&4: the nu update is left out (a[3..5], b[3..5], o[3..5] unused)
 template <int KIND> struct EpiKernel {
   typedef EpiParams Params;
   static constexpr int THREADS = 256;
@@ -111,34 +108,7 @@ template <int KIND> struct EpiKernel {
     if (!w.valid) return;
     const bool k0 = (w.k2 == 0.0);
     const double alpha = 1.0 / p.dt + w.k2 / (2.0 * p.Rm);
-    const double beta = 1.0 / p.dt - w.k2 / (2.0 * p.Rm);
-    if (KIND == EPI_FWD) {
-      C3 out = zero3();
-      if (!k0) {
-        const C3 B = load3(p.b, 0, idx);
-        const C3 F = curl3(w, load3(p.a, 0, idx));
-        out = proj_scale_minus(w, axpy3(beta, B, F), 1.0 / alpha, kdot_over_k2(w, B));
-      }
-      store3(p.o, 0, idx, out);
-    } else if (KIND == EPI_ADJ) {
-      C3 Gn = zero3(), Nn = zero3(), Wn = zero3();
-      if (!k0) {
-        const C3 G = load3(p.b, 0, idx);
-        C3 HG = load3(p.a, 0, idx);
-        if (p.flag & 1) HG = axpy3(-2.0, load3(p.o2, 3, idx), HG);
-        Gn = proj_scale_minus(w, axpy3(beta, G, HG), 1.0 / alpha, kdot_over_k2(w, G));
-        if (!(p.flag & 4)) {
-          // nu-system: alpha = beta = 1/dt, F = -HN  =>  nu' = P[nu - dt*HN] - k (k.nu)/k^2
-          const C3 Nu = load3(p.b, 3, idx);
-          const C3 HN = load3(p.a, 3, idx);
-          Nn = proj_scale_minus(w, axpy3(-p.dt, HN, Nu), 1.0, kdot_over_k2(w, Nu));
-        }
-        Wn = curl3(w, Gn);
-      }
-      store3(p.o, 0, idx, Gn);
-      if (!(p.flag & 4)) store3(p.o, 3, idx, Nn);
-      store3(p.o2, 0, idx, Wn);
-    } else if (KIND == EPI_COMPAT) {
+    if (KIND == EPI_COMPAT) {
       C3 G = zero3(), Wn = zero3();
       const C3 f = load3(p.b, 0, idx);
       if (p.flag & 2) {

@@ -3,8 +3,8 @@
 // kernel, one HBM round trip of the pencil data per time step.
 //
 // Replaces, per time step of FWD_Solve_KDyn.py:635-641 (forward) and :955-961 (adjoint), the sequence
-//   FftPass<-1> (p1 -> coefficients)  +  EpiKernel<EPI_FWD / EPI_ADJ>  +  FftPass<+1> (coefficients -> p1)
-// of the unfused path: the right-hand side coefficients never travel to HBM, the state (B^n | G, nu) is read once
+//   FftPass<-1> (p1 -> coefficients)  +  a pointwise update kernel  +  FftPass<+1> (coefficients -> p1)
+// of an unfused path (the first working version of this library): the right-hand side coefficients never travel to HBM, the state (B^n | G, nu) is read once
 // and written once, and what the next step needs on the grid side (B^{n+1} | curl G', B_f of the next snapshot)
 // goes straight from shared memory into the inverse transform.
 //
