@@ -144,6 +144,9 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* SMO_OPT_PEER_PULL: 0 (default) = peer-memory transposes are fused into the producers' stores (push over NVLink);
  * 1 = fused into the consumers' loads (cp.async straight out of the peers' buffers, stores stay local). */
 #define SMO_OPT_PEER_PULL 3
+/* SMO_OPT_L2_HINTS: 1 (default) = the pencil data exchanged between the y passes and the fused z step of a time step is
+ * stored evict_last / read evict_first (single rank), so that it can stay L2 resident between the launches. */
+#define SMO_OPT_L2_HINTS 4
 int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);

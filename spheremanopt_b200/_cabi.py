@@ -76,6 +76,7 @@ SMO_ADJOINT_CONTINUOUS = 1
 SMO_COST_INTEGRATED = 2
 SMO_OPT_KERNEL_SYNC = 2
 SMO_OPT_PEER_PULL = 3
+SMO_OPT_L2_HINTS = 4
 
 
 def bind(cdll):

@@ -59,6 +59,7 @@ struct PassParams {
   long long pull_off;
   const cplx* peer_in[MAXF][MAXP];
   XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
+  int hint_in, hint_out;    // L2 residency hints of the loads / stores (0 none, 1 evict_first, 2 evict_last; y passes only)
 };
 
 template <class F, int DIR, bool TFAST, int T_> struct FftPass {
@@ -76,7 +77,7 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
   static constexpr int IN_ELEMS = TFAST ? NIN * T_ : T_ * LENP;
   static constexpr int X_ELEMS = T_ * F::XP;
   static constexpr int BUF = (IN_ELEMS > X_ELEMS) ? IN_ELEMS : X_ELEMS;
-  static constexpr size_t SMEM = (size_t)(2 * BUF + M) * sizeof(cplx) + (size_t)M * sizeof(int);
+  static constexpr size_t SMEM = (size_t)(2 * BUF + M) * sizeof(cplx) + (size_t)M * sizeof(int) + 16;
   struct State {
     double re[F::RT], im[F::RT];
     int ooff[F::R2];   // output offset of the k2-th result of this thread (complex elements), -1 = dropped
@@ -86,6 +87,7 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
   SMO_HD static cplx* buf(unsigned char* smem, int which) { return reinterpret_cast<cplx*>(smem) + (size_t)which * BUF; }
   SMO_HD static cplx* twid(unsigned char* smem) { return reinterpret_cast<cplx*>(smem) + 2 * (size_t)BUF; }
   SMO_HD static int* segtab(unsigned char* smem) { return reinterpret_cast<int*>(twid(smem) + M); }
+  SMO_HD static unsigned long long* pols(unsigned char* smem) { return reinterpret_cast<unsigned long long*>(segtab(smem) + M); }
 
   SMO_HD static void split_tid(int tid, int& t, int& jj) {
     if (TFAST) { t = tid % T; jj = tid / T; } else { jj = tid % RT; t = tid / RT; }
@@ -116,7 +118,10 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
       const cplx* src = p.in[f] + (long long)a * p.in_sA + (long long)(p.b0 + b) * p.in_sB;
       if (TFAST && PAD && p.pull_mode == 2)
         src = p.peer_in[f][a / p.peer_rows] + p.pull_off + (long long)(a % p.peer_rows) * p.in_sA + (long long)(p.b0 + b) * p.in_sB;
-      if (TFAST) {
+      if (TFAST && p.hint_in) {
+        const unsigned long long pol = pols(c.smem)[0];
+        for (int row = jj; row < NIN; row += RT) cp_async16_hint(&B[row * T + t], src + (long long)row * p.in_sN, pol);
+      } else if (TFAST) {
         // rows of T adjacent lines: lane t walks along z (16 B each, T*16 B contiguous per row)
         for (int row = jj; row < NIN; row += RT) cp_async16(&B[row * T + t], src + (long long)row * p.in_sN);
       } else if (PAD || p.seglen <= 0) {
@@ -156,6 +161,7 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
       st.ooff[k2] = off;
     }
     st.it = 0;
+    if (c.tid == 0) { pols(c.smem)[0] = l2_policy(p.hint_in ? p.hint_in : 1); pols(c.smem)[1] = l2_policy(p.hint_out ? p.hint_out : 1); }
   }
 
   template <int PH>
@@ -228,10 +234,19 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
               dst = p.peer_out[f][a / p.peer_rows] + p.peer_off + (long long)(a % p.peer_rows) * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
             else
               dst = p.out[f] + (long long)a * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
+            if (p.hint_out) {
+              const unsigned long long pol = pols(c.smem)[1];
 #pragma unroll
-            for (int k2 = 0; k2 < R2; ++k2) {
-              const int off = st.ooff[k2];
-              if (PAD || off >= 0) dst[off] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
+              for (int k2 = 0; k2 < R2; ++k2) {
+                const int off = st.ooff[k2];
+                if (PAD || off >= 0) st_cplx_hint(dst + off, st.re[k2] * p.scale, st.im[k2] * p.scale, pol);
+              }
+            } else {
+#pragma unroll
+              for (int k2 = 0; k2 < R2; ++k2) {
+                const int off = st.ooff[k2];
+                if (PAD || off >= 0) dst[off] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
+              }
             }
           }
         }

@@ -456,6 +456,7 @@ struct smo_kdyn {
   // in-kernel hand-shakes of the peer-memory transposes (XSync): flag words [0..MAXP) barrier kernel, [MAXP..2MAXP) "p1
   // filled" (A, signalled by the forward y pass), [2MAXP..3MAXP) "p1t filled" (B, signalled by the z kernels)
   int inkernel_sync; unsigned long long epochA, epochB; unsigned int* counters;
+  int l2_hints;                 // 1: L2 residency hints on the pencil data of the time loops (single rank)
   int peer_pull;                // 0 (default, measured faster on 2 B200): producers push; 1: consumers pull from the peers' buffers
 };
 
@@ -662,9 +663,10 @@ template <int M> struct KdOps {
   }
   // p1t [Nh][Nc][nz] -> p2 [Nh][M][nz]   (zero-pad + inverse FFT along y) for the z range [z0, z0+nzc)
   static int inv_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1,
-                   int wait = XS_NONE) {
+                   int wait = XS_NONE, bool loop = false) {
     PassParams p; fill(p, h, nf);
     xs_wait(h, p.xs, wait);
+    if (loop && h->l2_hints && h->nranks == 1) p.hint_in = 1;     // pencils: last use
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
     p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
     p.in_sA = (long long)h->Nc * h->nz; p.in_sB = 1; p.in_sN = h->nz;
@@ -680,9 +682,10 @@ template <int M> struct KdOps {
     return rc;
   }
   static int fwd_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1,
-                   int sig = XS_NONE) {
+                   int sig = XS_NONE, bool loop = false) {
     PassParams p; fill(p, h, nf);
     xs_signal(h, p.xs, sig);
+    if (loop && h->l2_hints && h->nranks == 1) { p.hint_in = 1; p.hint_out = 2; }   // x-spectra: last use; pencils: keep for the z step
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
     p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
     p.in_sA = (long long)M * h->nz; p.in_sB = 1; p.in_sN = h->nz;
@@ -805,6 +808,7 @@ template <int M> struct KdOps {
     p.nsteps = 1; p.mode = mode; p.ntrip = 1;
     p.nlines = h->nkx * h->Nc; p.tiles = (p.nlines + TZS - 1) / TZS; p.nwork = p.tiles * p.ntrip;
     p.do_inv = do_inv ? 1 : 0;
+    p.l2_hints = (h->l2_hints && h->nranks == 1) ? 1 : 0;
     p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
     p.line_stride = h->nz; p.kfac = h->kfac; p.Rm = Rm; p.dt = dt; p.scale = 1.0 / M; p.tw = h->tw;
     if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
@@ -828,15 +832,15 @@ template <int M> struct KdOps {
     const int nzc = h->nz / nch;
     for (int ch = 0; ch < nch; ++ch) {
       const int z0 = ch * nzc, zc = nch > 1 ? nzc : -1;
-      TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, st, z0, zc, ch == 0 ? XS_B : XS_NONE));
+      TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, st, z0, zc, ch == 0 ? XS_B : XS_NONE, true));
       if (mode == 0) TRY(x_fwd(h, xs, st, z0, zc, integ));
       else TRY(x_adj(h, xs, st, z0, zc, integ));
-      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, zc, ch == nch - 1 ? XS_A : XS_NONE));
+      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, zc, ch == nch - 1 ? XS_A : XS_NONE, true));
     }
     return 0;
   }
   // first half of a forward step only: x-spectra of the state whose z-padded form sits in p1t
-  static int y_only(smo_kdyn* h, cplx* const* xs, rt_stream st) { return inv_y(h, h->p1t, xs, 3, st, 0, -1, XS_B); }
+  static int y_only(smo_kdyn* h, cplx* const* xs, rt_stream st) { return inv_y(h, h->p1t, xs, 3, st, 0, -1, XS_B, true); }
   static void efill(EpiParams& p, smo_kdyn* h, double Rm, double dt, int flag) {
     memset(&p, 0, sizeof p);
     p.nsteps = 1; p.n = (long long)h->csize; p.Nc = h->Nc; p.Pc = h->Pc; p.kmax = h->kmax; p.kx0 = h->kx0;
@@ -936,7 +940,7 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
   return 0;
 #endif
 }
-static int graph_opts(const smo_kdyn* h) { return (h->prof_which << 24) | 1 | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16); }
+static int graph_opts(const smo_kdyn* h) { return (h->prof_which << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16); }
 
 // ---- snapshot store ------------------------------------------------------------------------------------------------
 // Forward states are kept in the form the adjoint x pass consumes: their x-spectra on this rank's z-slab, [Nh][M][nz] per
@@ -1225,7 +1229,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->jparts = nullptr; h->jparts_cap = 0; h->jparts_used = 0;
   h->graphs = nullptr; h->capturing = 0; h->cap_a0 = h->cap_b0 = 0; h->epoch_dev = nullptr;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
-  h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0;
+  h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0; h->l2_hints = 1;
   for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
   for (int s2 = 0; s2 < MAXP; ++s2) h->peer_flags[s2] = nullptr;
   h->chunks_fwd = h->chunks_adj = 1;    // off by default (measured slower at 128^3: the passes are not HBM-bound enough to gain)
@@ -1439,6 +1443,7 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
   switch (key) {
     case SMO_OPT_KERNEL_SYNC: h->inkernel_sync = value ? 1 : 0; return 0;
     case SMO_OPT_PEER_PULL: h->peer_pull = value ? 1 : 0; return 0;
+    case SMO_OPT_L2_HINTS: h->l2_hints = value ? 1 : 0; return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic
       for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) { h->peer_p1[f][s2] = h->p1[f]; h->peer_p1t[f][s2] = h->p1t[f]; }
       return 0;

@@ -68,6 +68,39 @@ SMO_HD void prefetch_l2(const void* p) {
   (void)p;
 #endif
 }
+// L2 residency hints.  Between the y pass that writes the z-padded pencils, the fused z step that rewrites them and the y
+// pass that reads them back, 75 MB (128^3) of pencil data is produced and consumed within ~100 us: stored with evict_last and
+// read with evict_first it can stay in the 126 MB L2 instead of making two round trips through HBM, provided the streams
+// that are only touched once (x-spectra, coefficient states) are marked evict_first and do not push it out.
+// kind: 1 = evict_first, 2 = evict_last.
+SMO_HD unsigned long long l2_policy(int kind) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long pol;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#else
+  (void)kind;
+  return 0ull;
+#endif
+}
+SMO_HD void cp_async16_hint(void* sdst, const void* gsrc, unsigned long long pol) {
+#if defined(__CUDA_ARCH__)
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "l"(pol) : "memory");
+#else
+  (void)pol;
+  memcpy(sdst, gsrc, 16);
+#endif
+}
+SMO_HD void st_cplx_hint(cplx* p, double x, double y, unsigned long long pol) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(pol) : "memory");
+#else
+  (void)pol;
+  p->x = x; p->y = y;
+#endif
+}
 SMO_HD void cp_async_commit() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;" ::: "memory");

@@ -50,6 +50,7 @@ struct ZParams {
   long long pull_off;
   const cplx* peer_in[MAXF][MAXP];
   XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
+  int l2_hints;             // 1: pencil lines are read evict_first and written evict_last, the coefficient state evict_first
 };
 
 template <class F, int T_> struct ZStep {
@@ -62,7 +63,7 @@ template <class F, int T_> struct ZStep {
   static constexpr int MIN_BLOCKS = (F::RT > 16) ? 2 : SMO_ZS_MB;
   static constexpr bool WARP_OK = (32 % F::RT == 0);       // the RT threads of a line never straddle a warp
   static constexpr int LAND = 3 * T_ * M, WORK = 3 * T_ * XP, STATE = 3 * T_ * PC;
-  static constexpr size_t SMEM = (size_t)(LAND + WORK + STATE + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int);
+  static constexpr size_t SMEM = (size_t)(LAND + WORK + STATE + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int) + 16;
   static_assert(XP >= PC, "compact coefficient line must fit into the exchange line");
   struct State {
     double re[F::RT], im[F::RT];
@@ -77,6 +78,7 @@ template <class F, int T_> struct ZStep {
   SMO_HD static cplx* twid(unsigned char* s) { return stl(s) + STATE; }
   SMO_HD static int* segidx(unsigned char* s) { return reinterpret_cast<int*>(twid(s) + M); }   // n / seglen
   SMO_HD static int* segrem(unsigned char* s) { return segidx(s) + M; }                         // n % seglen
+  SMO_HD static unsigned long long* pols(unsigned char* s) { return reinterpret_cast<unsigned long long*>(segrem(s) + M); }
 
   SMO_HD static void split_tid(int tid, int& f, int& t, int& jj) {
     jj = tid % RT;
@@ -96,7 +98,10 @@ template <class F, int T_> struct ZStep {
     if (b >= p.nlines) return;
     cplx* Ld = land(c.smem) + (f * T + t) * M;
     const cplx* src = p.in[3 * trip + f] + (long long)b * p.line_stride;
-    if (p.seglen <= 0) {
+    if (p.seglen <= 0 && p.l2_hints) {
+      const unsigned long long pol = pols(c.smem)[0];
+      for (int e = jj; e < M; e += RT) cp_async16_hint(&Ld[e], src + e, pol);
+    } else if (p.seglen <= 0) {
       for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], src + e);
     } else if (p.pull_mode == 1) {
       const int* si = segidx(c.smem);
@@ -120,7 +125,12 @@ template <class F, int T_> struct ZStep {
     if (b >= p.nlines) return;
     cplx* Sd = stl(c.smem) + (f * T + t) * PC;
     const cplx* src = p.b[3 * trip + f] + (long long)b * p.Pc;
-    for (int e = jj; e < PC; e += RT) cp_async16(&Sd[e], src + e);
+    if (p.l2_hints) {
+      const unsigned long long pol = pols(c.smem)[0];
+      for (int e = jj; e < PC; e += RT) cp_async16_hint(&Sd[e], src + e, pol);
+    } else {
+      for (int e = jj; e < PC; e += RT) cp_async16(&Sd[e], src + e);
+    }
   }
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
     cplx* W = twid(c.smem);
@@ -131,6 +141,7 @@ template <class F, int T_> struct ZStep {
       si[m] = p.seglen > 0 ? m / p.seglen : 0;
       sr[m] = p.seglen > 0 ? m % p.seglen : m;
     }
+    if (c.tid == 0) { pols(c.smem)[0] = l2_policy(1); pols(c.smem)[1] = l2_policy(2); }
     st.it = 0;
   }
 
@@ -274,6 +285,14 @@ template <class F, int T_> struct ZStep {
           for (int k2 = 0; k2 < R2; ++k2) {
             const int k = jj + R1 * k2;
             p.peer_out[fo][si[k]][p.peer_off + line + sr[k]] = make_double2(st.re[k2], st.im[k2]);
+          }
+        } else if (p.l2_hints) {
+          cplx* dst = p.out[fo] + line;
+          const unsigned long long pol = pols(c.smem)[1];
+#pragma unroll
+          for (int k2 = 0; k2 < R2; ++k2) {
+            const int k = jj + R1 * k2;
+            st_cplx_hint(dst + ((long long)si[k] * p.blk + sr[k]), st.re[k2], st.im[k2], pol);
           }
         } else {
           cplx* dst = p.out[fo] + line;

@@ -33,6 +33,9 @@ C_ = (N // 2) * (N - 1) ** 2 * 16; P1 = (N // 2) * (N - 1) * M * 16; P2 = (N // 
 alg_f = 9 * C_ + 12 * P1 + 15 * P2; alg_a = 18 * C_ + 24 * P1 + 27 * P2
 import os
 chunk_sets = [tuple(int(v) for v in cs.split(",")) for cs in os.environ.get("CHUNKS", "1,1").split(";")]
+for k, v in os.environ.items():
+    if k.startswith("SMO_OPT_"):
+        lib.smo_kdyn_set_option(dom.h, int(k[8:]), int(v))
 if os.environ.get("GRAPH"):
     lib.smo_kdyn_use_graph(dom.h, 1)
 for _ in range(3):
