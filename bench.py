@@ -281,6 +281,8 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = 1e3 / ms_step
+    # size-independent checks of the result (identical for every GPU count: compare the lines of a scaling run)
+    gnorm = [kdyn.Inner_Prod_3(g[0], g[0], dom), kdyn.Inner_Prod_3(g[1], g[1], dom)]
 
     # ---- e2e: host vectors in, host gradients out (reference-facing Mode H) ----------------------------------
     Bh = torch.empty(3 * M ** 3, dtype=torch.float64, pin_memory=True)
@@ -318,7 +320,7 @@ def run_gpu(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args.workload, world),
             "dof_steps_per_s": 3 * N ** 3 * 2 * nit * value,
-            "J": -f,
+            "J": -f, "grad_norms": gnorm,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
