@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .devvec import DevVec, VecOps, _stream_ptr
+from .devvec import DevVec, VecOps, _stream_ptr, fingerprint
 
 
 def _dist():
@@ -271,6 +271,7 @@ def FWD_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost
                                                                 int(N_ITERS), X_FWD_DICT.ptr(), C.byref(J),
                                                                 _flags(Cost_function, "Discrete"), _stream_ptr()))
     X_FWD_DICT.valid = True
+    X_FWD_DICT.tag = (fingerprint(X0[0]), fingerprint(X0[1]), float(Rm), float(dt), int(N_ITERS), Cost_function)
     return (-1.) * domain.allreduce_sum(J.value)
 
 
@@ -278,6 +279,9 @@ def ADJ_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost
     """KD:766-1004.  Returns [dJ/dB0, dJ/dU] in the layout/type of X0."""
     if not X_FWD_DICT.valid:
         raise RuntimeError("ADJ_Solve_IVP_Lin needs the snapshots of a preceding FWD_Solve_IVP_Lin (KD:955-957)")
+    if getattr(X_FWD_DICT, "tag", None) != (fingerprint(X0[0]), fingerprint(X0[1]), float(Rm), float(dt), int(N_ITERS), Cost_function):
+        # the store was written for another X or other parameters (never happens in the reference optimiser): refill it
+        FWD_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost_function, Adjoint_type)
     gB = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
     gU = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
     with torch.cuda.device(domain.device):

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .devvec import DevVec, VecOps, _stream_ptr
+from .devvec import DevVec, VecOps, _stream_ptr, fingerprint
 
 PARAM_A = -0.3   # SH:309
 
@@ -147,12 +147,16 @@ def FWD_Solve_IVP_Lin(X_k, domain, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, filenam
     if filename is not None:
         raise NotImplementedError("restart from a dedalus checkpoint file (SH:459-460)")
     J = forward_batch(X_k[0], domain, dt, N_ITERS, X_FWD_DICT)
+    X_FWD_DICT.tag = (fingerprint(X_k[0]), float(dt), int(N_ITERS))
     Jh = J.cpu().numpy()
     return (-1.) * float(Jh[0]) if Jh.size == 1 else (-1.) * Jh
 
 
 def ADJ_Solve_IVP_Lin(X_k, domain, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, filename=None, Adjoint_type="Discrete"):
     """SH:598-729.  Returns [dJ/du0] in the layout/type of X_k[0]."""
+    if X_FWD_DICT.valid and getattr(X_FWD_DICT, "tag", None) != (fingerprint(X_k[0]), float(dt), int(N_ITERS)):
+        # the store was written for another X (never happens in the reference optimiser): refill it
+        FWD_Solve_IVP_Lin(X_k, domain, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, filename, Adjoint_type)
     G = adjoint_batch(domain, dt, N_ITERS, X_FWD_DICT, Adjoint_type)
     if isinstance(X_k[0], DevVec):
         return [DevVec(G)]

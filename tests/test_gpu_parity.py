@@ -278,6 +278,30 @@ def test_devvec_and_sphere_ops():
     assert relerr(u, osp.Update_vector(x, 0.7, d, 2.5, okd.Inner_Prod_3, (od,))) <= 1e-13
 
 
+def test_grad_f_refills_a_stale_store():
+    """Grad_f called for an X other than the one the store was filled for re-runs the forward solve"""
+    from spheremanopt_b200 import kdyn, sh23
+    od = osh.domain_sh23(64)
+    dom = sh23.Domain(64)
+    Xa, Xb = sh23_input(od, seed=1), sh23_input(od, seed=2)
+    st = sh23.GEN_BUFFER(dom, 20)
+    sh23.FWD_Solve_IVP_Lin([Xa], dom, 0.1, 20, 20, st)
+    g = sh23.ADJ_Solve_IVP_Lin([Xb], dom, 0.1, 20, 20, st)
+    D = osh.GEN_BUFFER(od, 20)
+    osh.FWD_Solve_IVP_Lin([Xb], od, 0.1, 20, 20, D)
+    assert relerr(g[0], osh.ADJ_Solve_IVP_Lin([Xb], od, 0.1, 20, 20, D)[0]) <= TOL
+    okd_ = okd.domain_kdyn(16)
+    kd = kdyn.Domain(16)
+    Ba, Bb, U = kdyn_field(okd_, 1), kdyn_field(okd_, 3), kdyn_field(okd_, 2)
+    ks = kdyn.GEN_BUFFER(16, kd, 4)
+    kdyn.FWD_Solve_IVP_Lin([Ba, U], kd, 1.0, 1e-3, 4, 4, ks)
+    gk = kdyn.ADJ_Solve_IVP_Lin([Bb, U], kd, 1.0, 1e-3, 4, 4, ks)
+    Dk = okd.GEN_BUFFER(16, okd_, 4)
+    okd.FWD_Solve_IVP_Lin([Bb, U], okd_, 1.0, 1e-3, 4, 4, Dk)
+    go = okd.ADJ_Solve_IVP_Lin([Bb, U], okd_, 1.0, 1e-3, 4, 4, Dk)
+    assert relerr(gk[0], go[0]) <= TOL and relerr(gk[1], go[1]) <= TOL
+
+
 def test_errors_are_loud():
     from spheremanopt_b200 import kdyn, sh23
     with pytest.raises(RuntimeError):
