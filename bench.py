@@ -39,6 +39,8 @@ WORKLOADS = {
     "kdyn24": (24, 1.0, 1e-3, 1000),
     # BASELINE config 5: 4096 independent SH23 problems (Npts=256, dt=0.1, T=50), M_0 swept over [0.05, 0.1], sharded over the GPUs
     "sh23ens": (256, None, 0.1, 500),
+    # BASELINE config 1: ONE SH23 problem (the reference's own CPU-runnable case): latency of one f + Grad_f pair
+    "sh23": (256, None, 0.1, 500),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
 # (profiles/r1g_kdyn128_adj_step_ncu.txt: 509.6 MB read + 185.4 MB written - it also reads the forward state from its
@@ -156,7 +158,7 @@ def run_reference(args):
     if rank != 0:
         return
     N, Rm, dt, nit = WORKLOADS[args.workload]
-    if args.workload == "sh23ens":
+    if args.workload in ("sh23ens", "sh23"):
         from oracle import sh23 as osh
         od, X0 = osh.Generate_IC(0.0725)
         D = osh.GEN_BUFFER(od, nit)
@@ -166,7 +168,7 @@ def run_reference(args):
         value = 2.0 / (time.perf_counter() - t0)
         info = {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": "numpy oracle, 2 of 4096 instances, serial"}
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 4096e3 / value, "higher_is_better": True, "scaling": "strong",
+                          "warmup": args.warmup, "ms_per_step": (4096e3 if args.workload == "sh23ens" else 1e3) / value, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": "SH23 ensemble (config 5), oracle sample"},
                           "cpu_baseline": info, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -355,11 +357,11 @@ def run_gpu_sh23ens(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from spheremanopt_b200 import _cabi, sh23
     lib = _cabi.load()
-    N, _, dt, nit = WORKLOADS["sh23ens"]
-    total = 4096
+    N, _, dt, nit = WORKLOADS[args.workload]
+    total = 4096 if args.workload == "sh23ens" else world      # config 1: one instance (per GPU: replicas only)
     nb = total // world
     dom, X0 = sh23.Generate_IC(0.0725, N, device="cuda:%d" % local)
-    M0 = np.linspace(0.05, 0.1, total)[rank * nb:(rank + 1) * nb]
+    M0 = (np.linspace(0.05, 0.1, total) if args.workload == "sh23ens" else np.full(total, 0.0725))[rank * nb:(rank + 1) * nb]
     X = torch.from_numpy(np.sqrt(M0 / 0.0725)[:, None] * X0[None, :]).to(dom.device).reshape(-1).contiguous()
     store = sh23.GEN_BUFFER(dom, nit, N, batch=nb)
 
@@ -419,8 +421,9 @@ def run_gpu_sh23ens(args):
     ach = alg_adj / (t_adj * 1e-3) / 1e9
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "SH23 ensemble: %d independent problems Npts=%d (grid %d), dt=%g, N_ITERS=%d, M_0 in [0.05,0.1], discrete adjoint; "
-                                   "one step = f + Grad_f of every instance; sharded %d per GPU, no collective" % (total, N, 2 * N, dt, nit, nb),
+            "config": {"workload": ("SH23 ensemble: %d independent problems" % total if total > world else "SH23 single problem (config 1; replicas only on > 1 GPU)")
+                                   + " Npts=%d (grid %d), dt=%g, N_ITERS=%d, M_0 in [0.05,0.1], discrete adjoint; "
+                                   "one step = f + Grad_f of every instance; sharded %d per GPU, no collective" % (N, 2 * N, dt, nit, nb),
                        "instances": total, "Npts": N, "N_ITERS": nit, "dof": N,
                        "cache": "snapshot store %.1f GB per GPU streams through HBM; the state of an instance lives in shared memory" % (nb * (nit + 1) * (N // 2) * 16 / 1e9)},
             "dof_steps_per_s": N * 2 * nit * value,
@@ -447,7 +450,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "sh23ens":
+    elif args.workload in ("sh23ens", "sh23"):
         run_gpu_sh23ens(args)
     else:
         run_gpu(args)
