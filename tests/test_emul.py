@@ -147,6 +147,38 @@ def test_kdyn_integrated_cost_emulated(L, adj, every):
     L.smo_kdyn_destroy(h)
 
 
+def test_host_buffer_entry_points_emulated(L):
+    """the *_host forms of the C ABI (what INTEGRATION.md's ctypes stub binds): handle-owned device buffers and snapshot store"""
+    od = okd.domain_kdyn(16)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    emul.check(L.smo_kdyn_create(C.byref(h), 16, od.L, 0, 1, None))
+    J = C.c_double()
+    gB, gU = np.zeros_like(B0), np.zeros_like(U)
+    emul.check(L.smo_kdyn_forward_host(h, emul.ptr(B0), emul.ptr(U), 2.0, 1e-3, 3, None, C.byref(J), 0, None))
+    emul.check(L.smo_kdyn_adjoint_host(h, 2.0, 1e-3, 3, None, emul.ptr(gB), emul.ptr(gU), 0, None))
+    D = okd.GEN_BUFFER(16, od, 3)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, 3, 3, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, 3, 3, D)
+    assert abs(-J.value - fo) <= TOL * abs(fo) and relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    out = np.zeros_like(B0)
+    emul.check(L.smo_kdyn_prep_host(h, emul.ptr(B0), emul.ptr(U), 2.0, 1e-3, 2, emul.ptr(out), None))
+    Bc = okd.FWD_Solve_IVP_Prep(B0, U, od, 2.0, 1e-3, 2)
+    assert relerr(out, okd.Field_to_Vec(od, *[od.to_grid_3d(c) for c in Bc])) <= TOL
+    L.smo_kdyn_destroy(h)
+    sd = osh.domain_sh23(64)
+    X = sh23_input(sd, seed=2)
+    hs = C.c_void_p()
+    emul.check(L.smo_sh23_create(C.byref(hs), 64, sd.L, -0.3))
+    Js = C.c_double(); G = np.zeros(sd.M)
+    emul.check(L.smo_sh23_forward_host(hs, emul.ptr(X), 1, 0.1, 10, None, C.byref(Js), None))
+    emul.check(L.smo_sh23_adjoint_host(hs, 1, 0.1, 10, None, emul.ptr(G), 0, None))
+    Ds = osh.GEN_BUFFER(sd, 10)
+    fs = osh.FWD_Solve_IVP_Lin([X], sd, 0.1, 10, 10, Ds)
+    assert abs(-Js.value - fs) <= TOL * abs(fs) and relerr(G, osh.ADJ_Solve_IVP_Lin([X], sd, 0.1, 10, 10, Ds)[0]) <= TOL
+    L.smo_sh23_destroy(hs)
+
+
 def test_vector_kernels_emulated(L):
     od = okd.domain_kdyn(16)
     n = 3 * od.M ** 3

@@ -308,6 +308,39 @@ def test_bitwise_reproducible_runs():
         assert torch.equal(J, ref[0]) and torch.equal(G, ref[1])
 
 
+def test_c_abi_host_entry_points():
+    """the ctypes stub of INTEGRATION.md, verbatim: numpy in / numpy out through the *_host entry points of the C ABI"""
+    import ctypes as C
+    from spheremanopt_b200 import _cabi
+    lib = _cabi.load()
+    od = okd.domain_kdyn(24)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    assert lib.smo_kdyn_create(C.byref(h), 24, 2 * np.pi, 0, 1, None) == 0
+    J = C.c_double()
+    gB, gU = np.zeros_like(B0), np.zeros_like(U)
+    Rm, dt, nit = 1.0, 1e-3, 7
+    assert lib.smo_kdyn_forward_host(h, B0.ctypes.data, U.ctypes.data, Rm, dt, nit, None, C.byref(J), 0, None) == 0, lib.smo_last_error()
+    assert lib.smo_kdyn_adjoint_host(h, Rm, dt, nit, None, gB.ctypes.data, gU.ctypes.data, 0, None) == 0, lib.smo_last_error()
+    D = okd.GEN_BUFFER(24, od, nit)
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
+    assert abs(-J.value - fo) <= TOL * abs(fo) and relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    assert lib.smo_kdyn_adjoint_host(h, Rm, dt, nit + 1, None, gB.ctypes.data, gU.ctypes.data, 0, None) != 0      # store too small: loud
+    lib.smo_kdyn_destroy(h)
+    sd = osh.domain_sh23(256)
+    X = sh23_input(sd, seed=2)
+    hs = C.c_void_p()
+    assert lib.smo_sh23_create(C.byref(hs), 256, sd.L, -0.3) == 0
+    Js = C.c_double(); G = np.zeros(sd.M)
+    assert lib.smo_sh23_forward_host(hs, X.ctypes.data, 1, 0.1, 60, None, C.byref(Js), None) == 0
+    assert lib.smo_sh23_adjoint_host(hs, 1, 0.1, 60, None, G.ctypes.data, 0, None) == 0
+    Ds = osh.GEN_BUFFER(sd, 60)
+    fs = osh.FWD_Solve_IVP_Lin([X], sd, 0.1, 60, 60, Ds)
+    assert abs(-Js.value - fs) <= TOL * abs(fs) and relerr(G, osh.ADJ_Solve_IVP_Lin([X], sd, 0.1, 60, 60, Ds)[0]) <= TOL
+    lib.smo_sh23_destroy(hs)
+
+
 def test_grad_f_refills_a_stale_store():
     """Grad_f called for an X other than the one the store was filled for re-runs the forward solve"""
     from spheremanopt_b200 import kdyn, sh23
