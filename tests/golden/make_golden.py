@@ -102,6 +102,13 @@ def main():
         dB, dU = kdyn_field(dom, 11), kdyn_field(dom, 12)
         out["taylor_kdyn_dB"] = taylor([B0, U], [dB, 0. * dU], okd.FWD_Solve_IVP_Lin, okd.ADJ_Solve_IVP_Lin, okd.Inner_Prod_3, args_f, (dom, None))
         out["taylor_kdyn_dBdU"] = taylor([B0, U], [dB, dU], okd.FWD_Solve_IVP_Lin, okd.ADJ_Solve_IVP_Lin, okd.Inner_Prod_3, args_f, (dom, None))
+        # ---- KDyn, Cost_function="Integrated" (KD:655-669, 738-742, 861-864): the reference's gradient test + digests
+        DI = okd.GEN_BUFFER(Npts, dom, nit)
+        args_i = [dom, 1.0, 1e-3, nit, nit, DI, "Integrated", "Discrete"]
+        out["taylor_kdyn_integrated"] = taylor([B0, U], [dB, dU], okd.FWD_Solve_IVP_Lin, okd.ADJ_Solve_IVP_Lin, okd.Inner_Prod_3, args_i, (dom, None))
+        fi = okd.FWD_Solve_IVP_Lin([B0, U], *args_i)
+        gi = okd.ADJ_Solve_IVP_Lin([B0, U], *args_i)
+        out["case_kdyn_N16_integrated"] = {"N_ITERS": nit, "f": fi, "gradB": digest(gi[0]), "gradU": digest(gi[1])}
         # ---- KDyn optimiser history, Npts = 16, 40 steps, 4 iterations of KD:1066's call
         RES, FUN, Xopt = SGD.Optimise_On_Multi_Sphere([B0, U], [1.0, 1.0], okd.FWD_Solve_IVP_Lin, okd.ADJ_Solve_IVP_Lin, okd.Inner_Prod_3,
                                                       args_f, (dom, None), max_iters=4, alpha_k=100., LS='LS_wolfe', CG=True,
@@ -113,7 +120,7 @@ def main():
     with open(os.path.join(HERE, "golden.json"), "w") as fh:
         json.dump(out, fh, indent=1)
     print("wrote", os.path.join(HERE, "golden.json"))
-    for k in ("taylor_sh23", "taylor_kdyn_dB", "taylor_kdyn_dBdU"):
+    for k in ("taylor_sh23", "taylor_kdyn_dB", "taylor_kdyn_dBdU", "taylor_kdyn_integrated"):
         print(k, "slopes R:", np.round(out[k][3][:4], 4), " R2:", np.round(out[k][4][:4], 4))
 
 

@@ -64,9 +64,22 @@ def test_initial_conditions_golden():
     digest_close(U, GOLD["ic_kdyn_N16"]["U"])
 
 
+def test_kdyn_integrated_golden():
+    g = GOLD["case_kdyn_N16_integrated"]
+    dom, B0, U = okd.Generate_IC(16, (0., 2. * np.pi), 1.0, True, Rm=1.0, dt=1e-3)
+    nit = g["N_ITERS"]
+    D = okd.GEN_BUFFER(16, dom, nit)
+    args = [dom, 1.0, 1e-3, nit, nit, D, "Integrated", "Discrete"]
+    f = okd.FWD_Solve_IVP_Lin([B0, U], *args)
+    assert abs(f - g["f"]) <= TOL * abs(g["f"])
+    gr = okd.ADJ_Solve_IVP_Lin([B0, U], *args)
+    digest_close(gr[0], g["gradB"])
+    digest_close(gr[1], g["gradU"])
+
+
 def test_golden_taylor_slopes_are_two():
     """the table saved by the unmodified reference Adjoint_Gradient_Test (make_golden.py): R ~ h, R2 ~ h^2"""
-    for key in ("taylor_sh23", "taylor_kdyn_dB", "taylor_kdyn_dBdU"):
+    for key in ("taylor_sh23", "taylor_kdyn_dB", "taylor_kdyn_dBdU", "taylor_kdyn_integrated"):
         AA = np.asarray(GOLD[key])
         assert np.all(np.abs(AA[3, :4] - 1.0) < 2e-2), key
         assert np.all(np.abs(AA[4, :4] - 2.0) < 1e-2), key
