@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """Headline benchmark: Grad_f evaluations per second (forward + discrete adjoint) of the kinematic dynamo.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload kdyn128|kdyn64|kdyn24]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload kdyn128|kdyn64|kdyn24|sh23ens|sh23]
+                    [--no-graph] [--no-cpu]
 
 One "step" = one Grad_f evaluation of BASELINE config 3: f(X) followed by Grad_f(X) (the reference's state coupling:
 Grad_f replays the snapshots f wrote), Npts = 128^3 (192^3 dealiased grid), Rm = 10, dt = 1e-3, N_ITERS = 1000 time
 steps each way, X = [B0, U] synthetic band-limited solenoidal fields (seeded).  The line printed by rank 0 follows the
 driver's contract; see DESIGN.md section "Measurement" for the definition of every key.
 
- * value  - device-resident vectors (DevVec), timed with CUDA events on the launching stream, max over ranks;
+ * value  - device-resident vectors (DevVec), timed with CUDA events on the launching stream, max over ranks; the time
+            loops are replayed from CUDA graphs captured during the warm-up (--no-graph: eager launches);
  * e2e    - the same pair through the reference-facing callables with HOST (pinned numpy) vectors in and numpy
             gradients out, H2D/D2H copies inside the timed region;
  * roofline - the dominant kernel (fused adjoint x-pass), CUDA-event timed per launch inside the timed region,
             algorithmic bytes per SURVEY.md section 8(d);
  * cpu_baseline - the numpy/scipy oracle (a port, not Dedalus) on the box's host cores, bounded sample.
+Other workloads (parity-test configurations of BASELINE.json, not the headline): sh23ens = config 5 (4096 SH23 problems in one
+batched launch each way), sh23 = config 1 (one SH23 problem), kdyn64 / kdyn24 = smaller dynamo grids.
 With --impl reference the same oracle is the timed arm (the reference's own Dedalus path cannot be installed: no
 dedalus/mpi4py/FFTW in the image and no network).
 """
