@@ -68,6 +68,18 @@ def _worker(rank, world, port, Npts, nit, q):
         eJ = abs(-Jt.item() - fo) / abs(fo)
         eB = float(np.abs(gB - slab(go[0])).max() / np.abs(go[0]).max())
         eU = float(np.abs(gU - slab(go[1])).max() / np.abs(go[1]).max())
+        # cost "Integrated" through the checkpointed sweep (every = 2): per-rank partial sums of |B^n|^2 and segment recomputation
+        ck = np.zeros(L.smo_kdyn_checkpoint_bytes(h, nit, 2) // 16, dtype=complex)
+        seg = np.zeros(L.smo_kdyn_segment_bytes(h, 2) // 16, dtype=complex)
+        emul.check(L.smo_kdyn_forward_ckpt(h, emul.ptr(Bs), emul.ptr(Us), 1.5, 1e-3, nit, 2, emul.ptr(ck), C.byref(J), 2, None))
+        emul.check(L.smo_kdyn_adjoint_ckpt(h, 1.5, 1e-3, nit, 2, emul.ptr(ck), emul.ptr(seg), emul.ptr(gB), emul.ptr(gU), 2, None))
+        Jt = torch.tensor([J.value], dtype=torch.float64)
+        dist.all_reduce(Jt)
+        fi = okd.FWD_Solve_IVP_Lin([B0, U], od, 1.5, 1e-3, nit, nit, D, "Integrated")
+        gi = okd.ADJ_Solve_IVP_Lin([B0, U], od, 1.5, 1e-3, nit, nit, D, "Integrated")
+        eJ = max(eJ, abs(-Jt.item() - fi) / abs(fi))
+        eB = max(eB, float(np.abs(gB - slab(gi[0])).max() / np.abs(gi[0]).max()))
+        eU = max(eU, float(np.abs(gU - slab(gi[1])).max() / np.abs(gi[1]).max()))
         q.put((rank, e_coef, eJ, eB, eU))
     finally:
         dist.destroy_process_group()
