@@ -27,7 +27,11 @@ template <int R1_, int R2_> struct Fac {
 template <int M> struct FacOf;
 template <> struct FacOf<24>  { typedef Fac<6, 4> type; };
 template <> struct FacOf<36>  { typedef Fac<6, 6> type; };
+#if defined(SMO_TEST_R24)   // test-only factorisation: exercises the 24-thread (one FFT per warp) code paths of M = 384 at a small size
+template <> struct FacOf<48>  { typedef Fac<24, 2> type; };
+#else
 template <> struct FacOf<48>  { typedef Fac<8, 6> type; };
+#endif
 template <> struct FacOf<64>  { typedef Fac<8, 8> type; };
 template <> struct FacOf<72>  { typedef Fac<9, 8> type; };
 template <> struct FacOf<96>  { typedef Fac<12, 8> type; };

@@ -244,14 +244,18 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
   static constexpr int NJ = NF * HP;
   static constexpr int R1 = F::R1, R2 = F::R2, M = F::M, RT = F::RT;
   static constexpr int NH = M / 3;                   // retained kx modes (dealias 3/2: Npts/2 = M/3)
-  static constexpr int FT = HP * RT;                 // threads per field
-  static constexpr int NARROW = HP * R2;             // active threads per field in the R2-thread stages
+  // lanes reserved per FFT: RT, or a whole warp when RT does not divide 32 (384 = 24 x 16: 24 stage threads) - an FFT is
+  // then private to one warp ("PAIRWARP": every warp owns one column pair of one field) and the warp-level barriers apply
+  static constexpr int LP = (RT > 16 && RT < 32) ? 32 : RT;
+  static constexpr bool PAIRWARP = (LP != RT);
+  static constexpr int FT = HP * LP;                 // threads per field
+  static constexpr int NARROW = HP * R2;             // active threads per field in the R2-thread stages (dense mapping)
   static constexpr int THREADS = NF * FT;
   static constexpr int NPHASES = 9;
   static constexpr int MIN_BLOCKS = (RT > 16) ? 1 : ((THREADS <= 96) ? 2 * SMO_X_MB : SMO_X_MB);
   static constexpr int XLEN = (F::XP > FS::XP) ? ((F::XP > M) ? F::XP : M) : ((FS::XP > M) ? FS::XP : M);
   static constexpr int XLP = XLEN + ((12 - XLEN % 8) % 8);   // pitch of one FFT's exchange region, = 4 (mod 8) 16-byte units
-  static constexpr bool WSYNC = (FT == 32);
+  static constexpr bool WSYNC = (FT == 32) || PAIRWARP;
   SMO_HD static constexpr int sync_after(int ph) { return (!WSYNC || ph == 3 || ph == 4) ? 2 : 1; }
   // The cp.async targets (spectral tile, velocity tile) are dense 128-byte lines with an XOR swizzle inside each
   // line instead of padded pitches: LDGSTS writes a line in one wavefront only when 8 lanes cover one ALIGNED line,
@@ -310,9 +314,17 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
     cplx* S = sin_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
     const int f = c.tid / FT;
-    for (int q = c.tid % FT; q < NH * T; q += FT) {
-      const int tc = q % T, row = q / T;
-      cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+    if constexpr (PAIRWARP) {   // the warp of pair pp streams in the two columns it assembles
+      const int pp = (c.tid % FT) / LP;
+      for (int q = c.tid % LP; q < NH * 2; q += LP) {
+        const int tc = 2 * pp + (q & 1), row = q >> 1;
+        cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+      }
+    } else {
+      for (int q = c.tid % FT; q < NH * T; q += FT) {
+        const int tc = q % T, row = q / T;
+        cp_async16(&S[si(f, row, tc)], p.sin[f] + (long long)row * p.ncols + col0 + tc);
+      }
     }
   }
   // running-sum tile of the field this warp produces (fields 3..5 only), consumed by phase 8 of the same work item
@@ -322,9 +334,17 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
     cplx* A = acc_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
     const cplx* src = p.sout[out_field(f)];
-    for (int q = c.tid % FT; q < NH * T; q += FT) {
-      const int tc = q % T, row = q / T;
-      cp_async16(&A[si(f - 3, row, tc)], src + (long long)row * p.ncols + col0 + tc);
+    if constexpr (PAIRWARP) {
+      const int pp = (c.tid % FT) / LP;
+      for (int q = c.tid % LP; q < NH * 2; q += LP) {
+        const int tc = 2 * pp + (q & 1), row = q >> 1;
+        cp_async16(&A[si(f - 3, row, tc)], src + (long long)row * p.ncols + col0 + tc);
+      }
+    } else {
+      for (int q = c.tid % FT; q < NH * T; q += FT) {
+        const int tc = q % T, row = q / T;
+        cp_async16(&A[si(f - 3, row, tc)], src + (long long)row * p.ncols + col0 + tc);
+      }
     }
   }
   SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
@@ -335,7 +355,7 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
   }
 
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
-    const cplx w = ldg_c(p.tw + (c.tid % FT) % RT);
+    const cplx w = ldg_c(p.tw + (((c.tid % FT) % LP) < RT ? ((c.tid % FT) % LP) : 0));
     st.wr = w.x; st.wi = w.y;
     st.jacc = 0.0;
     st.it = 0;
@@ -347,9 +367,10 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
     const cplx* U = su_buf(c.smem);
     const int f = c.tid / FT, tif = c.tid % FT;
     // wide mapping (R1 = RT threads per FFT) and narrow mapping (R2 threads per FFT, dense on the first lanes)
-    const int ppw = tif / RT, jw = tif % RT;
-    const int ppn = tif / R2, jn = tif % R2;
-    const bool nact = tif < NARROW;
+    const int ppw = tif / LP, jw = tif % LP;
+    const bool wact = !PAIRWARP || jw < RT;
+    const int ppn = PAIRWARP ? ppw : tif / R2, jn = PAIRWARP ? jw : tif % R2;
+    const bool nact = PAIRWARP ? (jw < R2) : (tif < NARROW);
     cplx* Xw = x_buf(c.smem) + (f * HP + ppw) * XLP;
     cplx* Xn = x_buf(c.smem) + (f * HP + (nact ? ppn : 0)) * XLP;
     const bool more = work + c.ncta < p.nwork;
@@ -388,19 +409,23 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
       if (more) load_sin(p, work + c.ncta, c);   // the spectral buffer was consumed in phase 1
       if (MODE == X_ADJ && p.accumulate) load_acc(p, work, c);
       cp_async_commit();
+      if (wact) {
 #pragma unroll
-      for (int j = 0; j < R2; ++j) {
-        const cplx v = Xw[j * F::SK + jw];
-        st.re[j] = v.x; st.im[j] = v.y;
+        for (int j = 0; j < R2; ++j) {
+          const cplx v = Xw[j * F::SK + jw];
+          st.re[j] = v.x; st.im[j] = v.y;
+        }
+        stage2<F, +1>(st.re, st.im);             // st[k2] = grid value of field f at row jw + R1*k2 (column pair ppw)
       }
-      stage2<F, +1>(st.re, st.im);               // st[k2] = grid value of field f at row jw + R1*k2 (column pair ppw)
     }
     if (PH == 3) {
+      if (wact) {
 #pragma unroll
-      for (int k2 = 0; k2 < R2; ++k2) Xw[jw + R1 * k2] = make_double2(st.re[k2], st.im[k2]);
+        for (int k2 = 0; k2 < R2; ++k2) Xw[jw + R1 * k2] = make_double2(st.re[k2], st.im[k2]);
+      }
       cp_async_wait<1>();                       // the velocity tile of this work item has landed
     }
-    if (PH == 4) {
+    if (PH == 4 && wact) {
       // component (out_field) of the cross product that contains this thread's own field; own values stay in registers
       const cplx* Xa = x_buf(c.smem) + ppw * XLP + jw;        // + field * HP * XLP + row
 #pragma unroll
@@ -443,8 +468,10 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
     if (PH == 5) {
       if (more) load_su(p, work + c.ncta, c);    // the velocity buffer was consumed in phase 4
       cp_async_commit();
+      if (wact) {
 #pragma unroll
-      for (int k1 = 0; k1 < R2; ++k1) Xw[jw * FS::SK + k1] = make_double2(st.re[k1], st.im[k1]);
+        for (int k1 = 0; k1 < R2; ++k1) Xw[jw * FS::SK + k1] = make_double2(st.re[k1], st.im[k1]);
+      }
     }
     if (PH == 6) {
       if (nact) {
@@ -468,13 +495,13 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
     }
     if (PH == 8) {
       // own thread order (column pairs fastest) so that a row's T columns are stored by adjacent lanes
-      const int pp8 = tif % HP, kk = tif / HP;
+      const int pp8 = PAIRWARP ? tif / LP : tif % HP, kk = PAIRWARP ? tif % LP : tif / HP;
       const cplx* X8 = x_buf(c.smem) + (f * HP + pp8) * XLP;
       cplx* O = p.sout[out_field(f)] + tile_of(p, work) * T + 2 * pp8;
       const double h = 0.5 * p.scale;
       const bool addto = (MODE == X_ADJ) && p.accumulate && f >= 3;
       const cplx* A = acc_buf(c.smem);
-      for (int k = kk; k < NH; k += RT) {
+      for (int k = kk; k < NH; k += LP) {
         const cplx zk = X8[k];
         const cplx zm = X8[(M - k) % M];
         cplx o0 = make_double2(h * (zk.x + zm.x), h * (zk.y - zm.y));

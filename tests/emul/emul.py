@@ -19,6 +19,7 @@ _CSRC = os.path.join(_ROOT, "spheremanopt_b200", "csrc")
 _OUT = os.path.join(_HERE, "_build", "libsmo_emul.so")
 
 _lib = None
+_variants = {}
 
 
 def _stale():
@@ -39,6 +40,20 @@ def lib():
             subprocess.run(cmd, check=True)
         _lib = _cabi.bind(C.CDLL(_OUT))
     return _lib
+
+
+def lib_variant(name, defines):
+    """a second build of the emulation library with extra -D switches (e.g. the test-only radix-24 factorisation of M = 48)"""
+    if name not in _variants:
+        out = os.path.join(_HERE, "_build", "libsmo_emul_%s.so" % name)
+        deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(_ROOT, "include", "smo_b200.h")]
+        if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            cmd = ["g++", "-O2", "-std=c++17", "-x", "c++", "-DSMO_EMUL"] + ["-D" + d for d in defines] + \
+                  ["-fPIC", "-shared", "-Wl,-Bsymbolic", "-o", out, os.path.join(_CSRC, "smo_api.cu")]
+            subprocess.run(cmd, check=True)
+        _variants[name] = _cabi.bind(C.CDLL(out))
+    return _variants[name]
 
 
 def ptr(a):

@@ -179,6 +179,31 @@ def test_host_buffer_entry_points_emulated(L):
     L.smo_sh23_destroy(hs)
 
 
+def test_kdyn_radix24_paths_emulated():
+    """the code paths of the 256^3 grid (M = 384 = 24 x 16: 24 stage threads per FFT, one FFT per warp in the fused x pass,
+    CTA-wide barriers in the y / z kernels) at a size the host emulation can afford: M = 48 factorised as 24 x 2"""
+    L24 = emul.lib_variant("r24", ["SMO_TEST_R24"])
+    Npts, nit = 32, 3
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    _cabi_check = lambda rc: emul._cabi.check(L24, rc)
+    _cabi_check(L24.smo_kdyn_create(C.byref(h), Npts, od.L, 0, 1, None))
+    gsz = L24.smo_kdyn_grid_elems(h)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    for cost, flag in (("Final", 0), ("Integrated", 2)):
+        snaps = np.zeros(L24.smo_kdyn_snapshot_bytes(h, nit) // 16, dtype=complex)
+        J = C.c_double()
+        gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
+        _cabi_check(L24.smo_kdyn_forward(h, emul.ptr(B0), emul.ptr(U), 2.0, 1e-3, nit, emul.ptr(snaps), C.byref(J), flag, None))
+        _cabi_check(L24.smo_kdyn_adjoint(h, 2.0, 1e-3, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), flag, None))
+        fo = okd.FWD_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D, cost)
+        go = okd.ADJ_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D, cost)
+        assert abs(-J.value - fo) <= TOL * abs(fo)
+        assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    L24.smo_kdyn_destroy(h)
+
+
 def test_vector_kernels_emulated(L):
     od = okd.domain_kdyn(16)
     n = 3 * od.M ** 3
