@@ -147,6 +147,12 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* SMO_OPT_L2_HINTS: 1 (default) = the pencil data exchanged between the y passes and the fused z step of a time step is
  * stored evict_last / read evict_first (single rank), so that it can stay L2 resident between the launches. */
 #define SMO_OPT_L2_HINTS 4
+/* SMO_OPT_PUSH_WAVES: n >= 1 (default 1): kernels that push their results into the peers' memory run about n work items per
+ * CTA one after the other, so that the remote stores of the first items drain over NVLink while the later ones compute. */
+#define SMO_OPT_PUSH_WAVES 5
+/* SMO_OPT_TWO_STREAMS: 1 = the z chunks of the y -> fused x -> y section (smo_kdyn_set_chunks) alternate between two CUDA
+ * streams, so that one chunk's NVLink transfer and hand-shake overlap the other chunk's x pass; 0 (default) = one stream. */
+#define SMO_OPT_TWO_STREAMS 6
 int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);
@@ -171,6 +177,11 @@ size_t smo_vec_work_bytes(long long n);
  * 1/M^3 gives the reference's grid mean).  Deterministic; synchronises the stream. */
 int smo_vec_dot(const double* x_dev, const double* y_dev, long long n, double scale, double* out_host,
                 void* work_dev, void* stream);
+/* the same without the D2H copy / synchronisation: the scaled sum is left in ((double*)work_dev)[0] */
+int smo_vec_dot_dev(const double* x_dev, const double* y_dev, long long n, double scale, void* work_dev, void* stream);
+/* 64-bit position-sensitive checksum of the bit patterns of x (sum_i bits(x_i)*(2i+1) mod 2^64): the host layer's identity check
+ * of the X a snapshot store was filled for (the f -> Grad_f coupling of SGD:740-796).  Synchronises the stream. */
+int smo_vec_checksum(const double* x_dev, long long n, unsigned long long* out_host, void* work_dev, void* stream);
 /* out = a*x + b*y (y may be NULL when b == 0): the numpy algebra of SGD:642, 659, 687-690, 772, 776 */
 int smo_vec_axpby(double a, const double* x_dev, double b, const double* y_dev, double* out_dev, long long n,
                   void* stream);
@@ -180,6 +191,11 @@ int smo_vec_project(const double* x_dev, const double* v_dev, double* out_dev, l
 /* Replaces Update_vector (SGD:661-690): f = x + alpha*d ; out = f*sqrt(M0/(scale*sum f_j^2)) */
 int smo_vec_retract(const double* x_dev, double alpha, const double* d_dev, double M0, double scale, double* out_dev,
                     long long n, void* work_dev, void* stream);
+
+/* measurement aid (bench.py): one launch of dependent fp64 FMA chains on every SM (ctas_per_sm x 256 threads, 8 chains each);
+ * *flops_out = flop of the launch.  Timed by the caller with CUDA events: the measured DFMA peak that the SH23 ensemble's
+ * fp64 roofline is quoted against.  out_dev: >= 256*ctas_per_sm*#SMs doubles (never written in practice). */
+int smo_microbench_dfma(double* out_dev, int iters, int ctas_per_sm, double* flops_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,9 @@ SIGNATURES = {
     # vectors
     "smo_vec_work_bytes": (sz, [ll]),
     "smo_vec_dot": (i32, [dp, dp, ll, f64, C.POINTER(f64), vp, vp]),
+    "smo_vec_dot_dev": (i32, [dp, dp, ll, f64, vp, vp]),
+    "smo_microbench_dfma": (i32, [dp, i32, i32, C.POINTER(f64), vp]),
+    "smo_vec_checksum": (i32, [dp, ll, C.POINTER(C.c_ulonglong), vp, vp]),
     "smo_vec_axpby": (i32, [f64, dp, f64, dp, dp, ll, vp]),
     "smo_vec_project": (i32, [dp, dp, dp, ll, vp, vp]),
     "smo_vec_retract": (i32, [dp, f64, dp, f64, f64, dp, ll, vp, vp]),
@@ -77,6 +80,8 @@ SMO_COST_INTEGRATED = 2
 SMO_OPT_KERNEL_SYNC = 2
 SMO_OPT_PEER_PULL = 3
 SMO_OPT_L2_HINTS = 4
+SMO_OPT_PUSH_WAVES = 5
+SMO_OPT_TWO_STREAMS = 6
 
 
 def bind(cdll):

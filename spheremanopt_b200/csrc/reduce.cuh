@@ -23,6 +23,7 @@ struct VecParams {
   long long n;
   double a, b, c;
   int op;
+  int vec2;                  // 1: x, y, out are 16-byte aligned -> 128-bit accesses
 };
 
 constexpr int VTHREADS = 256;
@@ -73,8 +74,35 @@ enum {
   V_RESCALE = 6   // out = out*sqrt(b/(c*s0))      with device scalar        (retraction, pass 2)
 };
 
+// one element of operation OP: reads xv / yv / the old output ov as the operation needs, returns the new output in ov
+template <int OP> SMO_HD void vec_elem(const VecParams& p, double s, double xv, double yv, double& ov, double& a0, double& a1) {
+  if (OP == V_DOT) a0 += xv * yv;
+  if (OP == V_DOT2) { a0 += xv * yv; a1 += xv * xv; }
+  if (OP == V_AXPBY) ov = p.a * xv + p.b * yv;
+  if (OP == V_SCALE) ov = p.a * xv;
+  if (OP == V_PROJ) ov = yv - s * xv;
+  if (OP == V_AXPY_NRM) { const double f = xv + p.a * yv; ov = f; a0 += f * f; }
+  if (OP == V_RESCALE) ov = ov * s;
+}
+template <int OP> struct VecTraits {
+  static constexpr bool RX = (OP != V_RESCALE);
+  static constexpr bool RY = (OP == V_DOT || OP == V_DOT2 || OP == V_AXPBY || OP == V_PROJ || OP == V_AXPY_NRM);
+  static constexpr bool RO = (OP == V_RESCALE);
+  static constexpr bool WO = (OP == V_AXPBY || OP == V_SCALE || OP == V_PROJ || OP == V_AXPY_NRM || OP == V_RESCALE);
+};
+SMO_HD double2 ld_pair(const double* p, long long i2) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(reinterpret_cast<const double2*>(p) + i2);
+#else
+  return make_double2(p[2 * i2], p[2 * i2 + 1]);
+#endif
+}
+
+// Streaming kernels: every thread moves 16 bytes per access (ld/st.global.v2.f64), 4 independent accesses per operand in
+// flight (p.vec2 = 1: all operands 16-byte aligned; else the scalar path).  HBM-bound: 2-3 vector passes per operation.
 template <int OP> struct VecKernel {
   typedef VecParams Params;
+  typedef VecTraits<OP> Tr;
   static constexpr int THREADS = VTHREADS;
   static constexpr int NPHASES = 2;
   static constexpr int MIN_BLOCKS = 1;
@@ -90,17 +118,37 @@ template <int OP> struct VecKernel {
       double s = 0.0;
       if (OP == V_PROJ) s = p.scalars[0] / p.scalars[1];
       if (OP == V_RESCALE) s = sqrt(p.b / (p.c * p.scalars[0]));
+      if (p.vec2) {
+        const long long n2 = p.n >> 1, base2 = base >> 1;
+        constexpr int NE = VCHUNK / 2 / VTHREADS;
 #pragma unroll 4
-      for (int e = 0; e < VCHUNK / VTHREADS; ++e) {
-        const long long i = base + (long long)e * VTHREADS + tid;
-        if (i < p.n) {
-          if (OP == V_DOT) a0 += p.x[i] * p.y[i];
-          if (OP == V_DOT2) { const double xv = p.x[i]; a0 += xv * p.y[i]; a1 += xv * xv; }
-          if (OP == V_AXPBY) p.out[i] = p.a * p.x[i] + p.b * p.y[i];
-          if (OP == V_SCALE) p.out[i] = p.a * p.x[i];
-          if (OP == V_PROJ) p.out[i] = p.y[i] - s * p.x[i];
-          if (OP == V_AXPY_NRM) { const double f = p.x[i] + p.a * p.y[i]; p.out[i] = f; a0 += f * f; }
-          if (OP == V_RESCALE) p.out[i] = p.out[i] * s;
+        for (int e = 0; e < NE; ++e) {
+          const long long i2 = base2 + (long long)e * VTHREADS + tid;
+          if (i2 < n2) {
+            double2 xv = make_double2(0.0, 0.0), yv = xv, ov = xv;
+            if (Tr::RX) xv = ld_pair(p.x, i2);
+            if (Tr::RY) yv = ld_pair(p.y, i2);
+            if (Tr::RO) ov = reinterpret_cast<const double2*>(p.out)[i2];
+            vec_elem<OP>(p, s, xv.x, yv.x, ov.x, a0, a1);
+            vec_elem<OP>(p, s, xv.y, yv.y, ov.y, a0, a1);
+            if (Tr::WO) reinterpret_cast<double2*>(p.out)[i2] = ov;
+          }
+        }
+        const long long last = p.n - 1;     // odd length: the unpaired last element
+        if ((p.n & 1) && tid == 0 && last >= base && last < base + VCHUNK) {
+          double ov = Tr::RO ? p.out[last] : 0.0;
+          vec_elem<OP>(p, s, Tr::RX ? p.x[last] : 0.0, Tr::RY ? p.y[last] : 0.0, ov, a0, a1);
+          if (Tr::WO) p.out[last] = ov;
+        }
+      } else {
+#pragma unroll 4
+        for (int e = 0; e < VCHUNK / VTHREADS; ++e) {
+          const long long i = base + (long long)e * VTHREADS + tid;
+          if (i < p.n) {
+            double ov = Tr::RO ? p.out[i] : 0.0;
+            vec_elem<OP>(p, s, Tr::RX ? p.x[i] : 0.0, Tr::RY ? p.y[i] : 0.0, ov, a0, a1);
+            if (Tr::WO) p.out[i] = ov;
+          }
         }
       }
       st.acc[0] = a0; st.acc[1] = a1;
@@ -139,6 +187,63 @@ struct FinalSum {
       double s = 0.0;
       for (int t = 0; t < VTHREADS; ++t) s += S[t];
       p.out[q] = p.a * s;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// 64-bit position-sensitive checksum of a vector's bit patterns: sum_i bits(x_i) * (2 i + 1) mod 2^64.  Used by the host
+// layer to notice that the snapshot store Grad_f is about to replay was written for a different X (the reference couples
+// f and Grad_f through that store); one streaming pass, deterministic, any single changed entry changes it.
+struct VecHash {
+  typedef VecParams Params;
+  static constexpr int THREADS = VTHREADS;
+  static constexpr int NPHASES = 2;
+  static constexpr int MIN_BLOCKS = 1;
+  static constexpr size_t SMEM = VTHREADS * sizeof(unsigned long long);
+  struct State {};
+  template <int PH>
+  SMO_HD static void phase(const Params& p, int work, int, int tid, unsigned char* smem, State&) {
+    unsigned long long* S = reinterpret_cast<unsigned long long*>(smem);
+    if (PH == 0) {
+      const long long base = (long long)work * VCHUNK;
+      unsigned long long a = 0ull;
+#pragma unroll 4
+      for (int e = 0; e < VCHUNK / VTHREADS; ++e) {
+        const long long i = base + (long long)e * VTHREADS + tid;
+        if (i < p.n) {
+          unsigned long long b;
+          const double v = p.x[i];
+          memcpy(&b, &v, sizeof b);
+          a += b * (2ull * (unsigned long long)i + 1ull);
+        }
+      }
+      S[tid] = a;
+    } else if (tid == 0) {
+      unsigned long long s = 0ull;
+      for (int t = 0; t < VTHREADS; ++t) s += S[t];
+      reinterpret_cast<unsigned long long*>(p.partials)[work] = s;
+    }
+  }
+};
+struct HashSum {
+  typedef SumParams Params;
+  static constexpr int THREADS = VTHREADS;
+  static constexpr int NPHASES = 2;
+  static constexpr int MIN_BLOCKS = 1;
+  static constexpr size_t SMEM = VTHREADS * sizeof(unsigned long long);
+  struct State {};
+  template <int PH> SMO_HD static void phase(const Params& p, int, int, int tid, unsigned char* smem, State&) {
+    unsigned long long* S = reinterpret_cast<unsigned long long*>(smem);
+    const unsigned long long* P = reinterpret_cast<const unsigned long long*>(p.partials);
+    if (PH == 0) {
+      unsigned long long s = 0ull;
+      for (int w = tid; w < p.npart; w += VTHREADS) s += P[w];
+      S[tid] = s;
+    } else if (tid == 0) {
+      unsigned long long s = 0ull;
+      for (int t = 0; t < VTHREADS; ++t) s += S[t];
+      reinterpret_cast<unsigned long long*>(p.out)[0] = s;
     }
   }
 };

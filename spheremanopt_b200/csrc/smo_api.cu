@@ -102,7 +102,7 @@ static int rt_memset(void* d, int v, size_t n, rt_stream) { memset(d, v, n); ret
 static int rt_sync(rt_stream) { return 0; }
 static int rt_check(const char*) { return 0; }
 template <class K> static int grid_for(int nwork) { return nwork < 3 ? nwork : 3; }
-template <class K> static int launch(const typename K::Params& p, rt_stream) {
+template <class K> static int launch(const typename K::Params& p, rt_stream, int /*waves*/ = 1) {
   if (p.nwork <= 0) return 0;
   const int grid = p.nwork < 3 ? p.nwork : 3;   // > 1 work item per CTA exercises the persistent loop
   emul_kernel<K>(grid, K::SMEM, p);
@@ -137,34 +137,51 @@ static int rt_check(const char* what) {
   if (e != cudaSuccess) return fail(SMO_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return 0;
 }
-static int g_num_sms = 0;
+// Launch configuration is cached PER DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device attribute, so a
+// second Domain on another GPU of the same process must set it again.
+constexpr int SMO_MAX_DEVICES = 64;
+static int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < SMO_MAX_DEVICES) ? dev : 0;
+}
+static int num_sms() {
+  static int v[SMO_MAX_DEVICES] = {0};
+  const int dev = cur_device();
+  if (v[dev] == 0) {
+    cudaDeviceGetAttribute(&v[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (v[dev] <= 0) v[dev] = 148;
+  }
+  return v[dev];
+}
 template <class K> struct LaunchCfg {
   static int blocks_per_sm() {
-    static int v = -1;
-    if (v < 0) {
+    static int v[SMO_MAX_DEVICES] = {0};
+    const int dev = cur_device();
+    if (v[dev] == 0) {
       if (K::SMEM > 48 * 1024)
         cudaFuncSetAttribute(smo_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smo_kernel<K>, K::THREADS, K::SMEM);
-      v = nb > 0 ? nb : 1;
+      v[dev] = nb > 0 ? nb : 1;
     }
-    return v;
+    return v[dev];
   }
 };
 // persistent-style grid: at most one resident wave (a multiple of the SM count), CTAs loop over work items
 template <class K> static int grid_for(int nwork) {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  const long long cap = (long long)g_num_sms * LaunchCfg<K>::blocks_per_sm();
+  const long long cap = (long long)num_sms() * LaunchCfg<K>::blocks_per_sm();
   return (int)(nwork < cap ? nwork : cap);
 }
-template <class K> static int launch(const typename K::Params& p, rt_stream st) {
+// waves > 1: the grid is shrunk so that every CTA handles about `waves` work items one after the other (kernels that push
+// their results to peer GPUs: the remote stores of a CTA's first item drain while it transforms the next one)
+template <class K> static int launch(const typename K::Params& p, rt_stream st, int waves = 1) {
   if (p.nwork <= 0) return 0;
-  const int grid = grid_for<K>(p.nwork);
+  int grid = grid_for<K>(p.nwork);
+  if (waves > 1) {
+    const int g2 = (p.nwork + waves - 1) / waves;
+    if (g2 < grid) grid = g2 > 0 ? g2 : 1;
+  }
   smo_kernel<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
   g_launches++;
   return rt_check("kernel launch");
@@ -212,6 +229,7 @@ static int vec_launch(const double* x, const double* y, double* out, long long n
   p.nwork = vec_nwork(n); p.nsteps = 1;
   p.partials = work ? work + 8 : nullptr;
   p.scalars = work;
+  p.vec2 = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)out) & 15) == 0) ? 1 : 0;
   return launch<VecKernel<OP>>(p, st);
 }
 static int final_sum(double* work, long long n, int nq, double a, rt_stream st) {
@@ -228,6 +246,28 @@ extern "C" int smo_vec_dot(const double* x, const double* y, long long n, double
   TRY((vec_launch<V_DOT>(x, y, nullptr, n, 0, 0, 0, w, st)));
   TRY(final_sum(w, n, 1, scale, st));
   TRY(rt_d2h(out_host, w, sizeof(double), st));
+  return rt_sync(st);
+}
+// the same without the D2H copy and the synchronisation: the scaled sum stays in work_dev[0] (double)
+extern "C" int smo_vec_dot_dev(const double* x, const double* y, long long n, double scale, void* work, void* stream) {
+  if (!x || !y || !work || n <= 0) return fail(SMO_E_ARG, "smo_vec_dot_dev: bad argument");
+  rt_stream st = (rt_stream)stream;
+  double* w = (double*)work;
+  TRY((vec_launch<V_DOT>(x, y, nullptr, n, 0, 0, 0, w, st)));
+  return final_sum(w, n, 1, scale, st);
+}
+extern "C" int smo_vec_checksum(const double* x, long long n, unsigned long long* out_host, void* work, void* stream) {
+  if (!x || !out_host || !work || n <= 0) return fail(SMO_E_ARG, "smo_vec_checksum: bad argument");
+  rt_stream st = (rt_stream)stream;
+  double* w = (double*)work;
+  VecParams p;
+  memset(&p, 0, sizeof p);
+  p.x = x; p.n = n; p.nwork = vec_nwork(n); p.nsteps = 1; p.partials = w + 8;
+  TRY(launch<VecHash>(p, st));
+  SumParams sp;
+  sp.partials = w + 8; sp.out = w; sp.nwork = 1; sp.nsteps = 1; sp.npart = vec_nwork(n); sp.nq = 1; sp.a = 1.0;
+  TRY(launch<HashSum>(sp, st));
+  TRY(rt_d2h(out_host, w, sizeof(unsigned long long), st));
   return rt_sync(st);
 }
 extern "C" int smo_vec_axpby(double a, const double* x, double b, const double* y, double* out, long long n,
@@ -253,6 +293,40 @@ extern "C" int smo_vec_retract(const double* x, double alpha, const double* d, d
   TRY((vec_launch<V_AXPY_NRM>(x, d, out, n, alpha, 0, 0, w, st)));
   TRY(final_sum(w, n, 1, 1.0, st));
   return vec_launch<V_RESCALE>(nullptr, nullptr, out, n, 0, M0, scale, w, st);
+}
+
+// ---- measured fp64 FMA peak (denominator of the SH23 ensemble's fp64 roofline) -----------------------------
+#if !defined(SMO_EMUL)
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (double)(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fma(v[i], a, b);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true for the operands used: keeps the chains alive
+}
+#endif
+// runs 2*64*iters flop per thread on ctas_per_sm * #SMs CTAs of 256 threads; *flops_out = total flop of the launch
+extern "C" int smo_microbench_dfma(double* out_dev, int iters, int ctas_per_sm, double* flops_out, void* stream) {
+#if !defined(SMO_EMUL)
+  if (!out_dev || iters <= 0 || ctas_per_sm <= 0) return fail(SMO_E_ARG, "smo_microbench_dfma: bad argument");
+  const int grid = num_sms() * ctas_per_sm;
+  dfma_peak_kernel<<<grid, 256, 0, (rt_stream)stream>>>(out_dev, iters, 0.999999, 1e-9);
+  g_launches++;
+  if (flops_out) *flops_out = 2.0 * 64.0 * (double)iters * 256.0 * (double)grid;
+  return rt_check("dfma microbenchmark launch");
+#else
+  (void)out_dev; (void)iters; (void)ctas_per_sm; (void)flops_out; (void)stream;
+  return fail(SMO_E_UNSUPPORTED, "no microbenchmarks in the host emulation");
+#endif
 }
 
 // ============================================================================================================
@@ -428,7 +502,7 @@ struct smo_kdyn {
   cplx* p2[MAXF];    // [Nh][M][nz]
   cplx* cw[MAXF];    // coefficient work
   cplx* G[3]; cplx* NU[3]; cplx* W[3];
-  double* jparts; size_t jparts_cap; size_t jparts_used;   // cost "Integrated": per-CTA partial sums of |B^n|^2 of every x pass
+  double* jparts; size_t jparts_cap; size_t jparts_used; size_t jparts_need;   // cost "Integrated": per-CTA partial sums of |B^n|^2 of every x pass
   cplx* acc[3];      // [Nh][M][nz] running sum over the adjoint steps of the x-spectra of (curl G) x B_f (allocated on first use)
   double* Ug[3];     // projected velocity on the grid [M][M][nz]
   double* Ut;        // the same, tile-major [M*nz/4][3][M][4] (read by the fused x passes)
@@ -458,7 +532,27 @@ struct smo_kdyn {
   int inkernel_sync; unsigned long long epochA, epochB; unsigned int* counters;
   int l2_hints;                 // 1: L2 residency hints on the pencil data of the time loops (single rank)
   int peer_pull;                // 0 (default, measured faster on 2 B200): producers push; 1: consumers pull from the peers' buffers
+  int push_waves;               // pushing kernels run ~push_waves work items per CTA so that remote stores drain under compute
+  int two_streams;              // 1: the z chunks of the y -> x -> y section alternate between two streams (transfers of one
+                                // chunk overlap the x pass of the next)
+  unsigned int* err_host; unsigned int* err_dev;   // host-mapped error word of the bounded hand-shake waits
+#if !defined(SMO_EMUL)
+  cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
+#endif
 };
+// flag words of one rank: [which][chunk][source rank]; which = 0 barrier kernel, XS_A, XS_B
+constexpr int MAXCH = 4;
+constexpr int NFLAGW = 3 * MAXCH * MAXP;
+
+// bounded hand-shake waits (smo_common.cuh: xs_spin) raise a host-mapped word instead of hanging the box
+static int kd_check_err(smo_kdyn* h, const char* who) {
+#if !defined(SMO_EMUL)
+  if (h->err_host && *(volatile unsigned int*)h->err_host)
+    return fail(SMO_E_COMM, "%s: a cross-GPU hand-shake wait timed out (a peer rank died or stalled); results of this handle are invalid", who);
+#endif
+  (void)h; (void)who;
+  return 0;
+}
 
 enum { PK_Z = 1, PK_Y = 2, PK_X = 3, PK_EPI = 4, PK_A2A = 5, PK_XA = 6, PK_ZS = 7 };
 
@@ -575,12 +669,18 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 #define SMO_TZS 2
 #endif
 // ---- CUDA graphs ----------------------------------------------------------------------------------------------
+// hsh = hash over EVERY buffer pointer the steps of the loop touch (checkpoint slots depend on `every`, which the first /
+// last pointers alone do not pin down: two CheckpointStores of equal size but different spacing must not share a graph)
 struct GraphKey {
-  int kind, n, opts; const void* p0; const void* p1; const void* p2; double Rm, dt;
+  int kind, n, opts; const void* p0; const void* p1; const void* p2; double Rm, dt; unsigned long long hsh;
   bool operator==(const GraphKey& o) const {
-    return kind == o.kind && n == o.n && opts == o.opts && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 && Rm == o.Rm && dt == o.dt;
+    return kind == o.kind && n == o.n && opts == o.opts && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 && Rm == o.Rm && dt == o.dt && hsh == o.hsh;
   }
 };
+static unsigned long long hash_ptr(unsigned long long hsh, const void* q) {
+  hsh ^= (unsigned long long)(uintptr_t)q + 0x9e3779b97f4a7c15ull + (hsh << 6) + (hsh >> 2);
+  return hsh;
+}
 #if !defined(SMO_EMUL)
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; unsigned long long nA, nB; long long nlaunch; size_t ev0, ev1; };
 struct GraphCache { std::vector<GraphEntry> e; cudaStream_t stream; cudaEvent_t ev0, ev1; };
@@ -592,21 +692,25 @@ struct GraphCache { int unused; };
 // ---- in-kernel hand-shakes ----------------------------------------------------------------------------------
 enum { XS_NONE = 0, XS_A = 1, XS_B = 2 };
 static bool kernel_sync(const smo_kdyn* h) { return h->peer_on && h->inkernel_sync; }
-// the launch about to be issued publishes "buffer `which` of every peer is filled by this rank" when it has finished
-static void xs_signal(smo_kdyn* h, XSync& xs, int which) {
+// the launch about to be issued publishes "buffer `which` (z chunk `chunk`) of every peer is filled by this rank" when it has
+// finished.  Epochs: one per transpose (all chunks of one transpose carry the same epoch; xs_next_epoch starts a new one).
+static unsigned long long xs_next_epoch(smo_kdyn* h, int which) { return (which == XS_A) ? ++h->epochA : ++h->epochB; }
+static void xs_signal(smo_kdyn* h, XSync& xs, int which, int chunk = 0, unsigned long long epoch = 0) {
   if (which == XS_NONE || !kernel_sync(h)) return;
   xs.sig_n = h->nranks; xs.sig_rank = h->rank; xs.sig_sys = h->peer_pull ? 0 : 1;
-  xs.sig_epoch = (which == XS_A) ? ++h->epochA : ++h->epochB;
+  xs.sig_epoch = epoch ? epoch : xs_next_epoch(h, which);
   if (h->capturing) { xs.sig_epoch -= (which == XS_A) ? h->cap_a0 : h->cap_b0; xs.sig_base = h->epoch_dev + which; }
-  for (int s = 0; s < h->nranks; ++s) xs.sig_flags[s] = h->peer_flags[s] + which * MAXP;
-  xs.counter = h->counters + which;
+  for (int s = 0; s < h->nranks; ++s) xs.sig_flags[s] = h->peer_flags[s] + (which * MAXCH + chunk) * MAXP;
+  xs.counter = h->counters + which * MAXCH + chunk;
+  xs.err = h->err_dev;
 }
-// the launch about to be issued first waits for the latest signal `which` of every rank
-static void xs_wait(smo_kdyn* h, XSync& xs, int which) {
+// the launch about to be issued first waits for the latest signal `which` (all `nch` chunks of it) of every rank
+static void xs_wait(smo_kdyn* h, XSync& xs, int which, int nch = 1) {
   if (which == XS_NONE || !kernel_sync(h)) return;
-  xs.wait_flags = h->flags + which * MAXP; xs.wait_n = h->nranks;
+  xs.wait_flags = h->flags + which * MAXCH * MAXP; xs.wait_n = h->nranks * nch; xs.wait_per = h->nranks;
   xs.wait_epoch = (which == XS_A) ? h->epochA : h->epochB;
   if (h->capturing) { xs.wait_epoch -= (which == XS_A) ? h->cap_a0 : h->cap_b0; xs.wait_base = h->epoch_dev + which; }
+  xs.err = h->err_dev;
 }
 
 // ---- pass launchers ---------------------------------------------------------------------------------------
@@ -638,7 +742,7 @@ template <int M> struct KdOps {
     }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Z, st);
-    int rc = launch<FftPass<F, +1, false, TZ>>(p, st);
+    int rc = launch<FftPass<F, +1, false, TZ>>(p, st, p.peer_mode ? h->push_waves : 1);
     prof_end(h, PK_Z, st);
     return rc;
   }
@@ -665,7 +769,7 @@ template <int M> struct KdOps {
   static int inv_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1,
                    int wait = XS_NONE, bool loop = false) {
     PassParams p; fill(p, h, nf);
-    xs_wait(h, p.xs, wait);
+    xs_wait(h, p.xs, wait);     // (the z kernels signal with one launch: chunk word 0)
     if (loop && h->l2_hints && h->nranks == 1) p.hint_in = 1;     // pencils: last use
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
     p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
@@ -682,9 +786,9 @@ template <int M> struct KdOps {
     return rc;
   }
   static int fwd_y(smo_kdyn* h, const cplx* const* in, cplx* const* out, int nf, rt_stream st, int z0 = 0, int nzc = -1,
-                   int sig = XS_NONE, bool loop = false) {
+                   int sig = XS_NONE, bool loop = false, int chunk = 0, unsigned long long epoch = 0) {
     PassParams p; fill(p, h, nf);
-    xs_signal(h, p.xs, sig);
+    xs_signal(h, p.xs, sig, chunk, epoch);
     if (loop && h->l2_hints && h->nranks == 1) { p.hint_in = 1; p.hint_out = 2; }   // x-spectra: last use; pencils: keep for the z step
     for (int f = 0; f < nf; ++f) { p.in[f] = in[f]; p.out[f] = out[f]; }
     p.nA = h->Nh; p.b0 = z0; p.nB = nzc < 0 ? h->nz : nzc; p.tilesB = (p.nB + TY - 1) / TY;
@@ -697,7 +801,7 @@ template <int M> struct KdOps {
     }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Y, st);
-    int rc = launch<FftPass<F, -1, true, TY>>(p, st);
+    int rc = launch<FftPass<F, -1, true, TY>>(p, st, p.peer_mode ? h->push_waves : 1);
     prof_end(h, PK_Y, st);
     return rc;
   }
@@ -737,18 +841,25 @@ template <int M> struct KdOps {
       p.tiles_per_row = nzc / T; p.row_tiles = h->nz / T; p.tile0 = z0 / T; p.nwork = M * p.tiles_per_row;
     }
   }
+  // cost "Integrated": partial-sum slots one forward step needs = sum over its z chunks of the x-pass grids (exact)
+  static size_t jparts_per_step(smo_kdyn* h) {
+    const int nch = yxy_chunks(h, 0);
+    XFParams p; xffill(p, h, 4, 0, nch > 1 ? h->nz / nch : -1);
+    return (size_t)nch * (size_t)grid_for<XFused<F, X_FWD, true>>(p.nwork);
+  }
   // forward: x-spectra of B (the snapshot slot or the work arrays) in, x-spectra of U x B out (work arrays)
   static int x_fwd(smo_kdyn* h, cplx* const* bp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
     XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = bp2[f]; p.sout[f] = h->p2[f]; }
-    prof_begin(h, PK_X, st);
     int rc;
     if (integ) {   // cost "Integrated": this launch's per-CTA sums of |B|^2 go to the next free slots of jparts
       const int grid = grid_for<XFused<F, X_FWD, true>>(p.nwork);
       if (h->jparts_used + (size_t)grid > h->jparts_cap) return fail(SMO_E_STATE, "x_fwd: partial-sum buffer too small");
       p.jpart = h->jparts + h->jparts_used; h->jparts_used += (size_t)grid;
+      prof_begin(h, PK_X, st);
       rc = launch<XFused<F, X_FWD, true>>(p, st);
     } else {
+      prof_begin(h, PK_X, st);
       rc = launch<XFused<F, X_FWD>>(p, st);
     }
     prof_end(h, PK_X, st);
@@ -794,9 +905,10 @@ template <int M> struct KdOps {
   }
   // fused z step (zstep.cuh): p1 -> [forward z FFT, implicit update of the state, inverse z FFT] -> p1
   //   mode 0: state Bn -> Bnp1, next operand Bnp1;  mode 1: state G in place, next operand curl G'
-  static int zstep(smo_kdyn* h, int mode, const cplx* const* Bn, cplx* const* Bnp1, bool do_inv, double Rm, double dt, rt_stream st) {
+  static int zstep(smo_kdyn* h, int mode, const cplx* const* Bn, cplx* const* Bnp1, bool do_inv, double Rm, double dt, rt_stream st,
+                   int nch_wait = 1) {
     ZParams p; memset(&p, 0, sizeof p);
-    xs_wait(h, p.xs, XS_A);
+    xs_wait(h, p.xs, XS_A, nch_wait);
     if (do_inv) xs_signal(h, p.xs, XS_B);
     const int nf = 3;
     for (int f = 0; f < nf; ++f) { p.in[f] = h->p1[f]; p.out[f] = h->p1[f]; }
@@ -820,23 +932,50 @@ template <int M> struct KdOps {
       for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_in[f][s2] = h->peer_p1t[f][s2];
     }
     prof_begin(h, PK_ZS, st);
-    int rc = launch<ZStep<F, TZS>>(p, st);
+    int rc = launch<ZStep<F, TZS>>(p, st, (p.peer_mode && do_inv) ? h->push_waves : 1);
     prof_end(h, PK_ZS, st);
     return rc;
   }
   // y -> fused x -> y part of a step: p1t (z-slab side) -> p1t.  xs = x-spectra of the forward state: WRITTEN by the inverse
   // y pass of a forward step (the snapshot slot of state n, or the work arrays), READ by the x pass of an adjoint step.
   // (with in-kernel hand-shakes the first y pass waits for "p1t filled", the last one signals "p1 filled")
-  static int yxy(smo_kdyn* h, int mode, cplx* const* xs, rt_stream st, bool integ = false) {
+  static int yxy_chunks(smo_kdyn* h, int mode) {
     const int nch = pick_chunks(h, mode == 0 ? h->chunks_fwd : h->chunks_adj, mode == 0 ? 3 : 6, TY > 4 ? TY : 4);
+    return (kernel_sync(h) && nch > MAXCH) ? 1 : nch;   // (one hand-shake flag word per chunk)
+  }
+  static int yxy(smo_kdyn* h, int mode, cplx* const* xs, rt_stream st, bool integ = false) {
+    const int nch = yxy_chunks(h, mode);
     const int nzc = h->nz / nch;
+    // every chunk's last y pass signals "p1 filled" on its own flag word with the same epoch; the z step waits for all of them
+    const unsigned long long eA = kernel_sync(h) ? xs_next_epoch(h, XS_A) : 0ull;
+#if !defined(SMO_EMUL)
+    // two streams: odd chunks run on an auxiliary stream, so that the remote stores (and the hand-shake) of one chunk's last
+    // y pass drain while the other chunk is still in its x pass.  Works eagerly and inside a stream capture (fork / join events).
+    const bool two = h->two_streams && nch > 1;
+    if (two && !h->aux_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    if (two) { CUDA_TRY(cudaEventRecord(h->ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0)); }
+#else
+    const bool two = false;
+#endif
     for (int ch = 0; ch < nch; ++ch) {
       const int z0 = ch * nzc, zc = nch > 1 ? nzc : -1;
-      TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, st, z0, zc, ch == 0 ? XS_B : XS_NONE, true));
-      if (mode == 0) TRY(x_fwd(h, xs, st, z0, zc, integ));
-      else TRY(x_adj(h, xs, st, z0, zc, integ));
-      TRY(fwd_y(h, h->p2, h->p1t, 3, st, z0, zc, ch == nch - 1 ? XS_A : XS_NONE, true));
+#if !defined(SMO_EMUL)
+      rt_stream q = (two && (ch & 1)) ? h->aux_stream : st;
+#else
+      rt_stream q = st;
+#endif
+      TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, q, z0, zc, (ch == 0 || two) ? XS_B : XS_NONE, true));
+      if (mode == 0) TRY(x_fwd(h, xs, q, z0, zc, integ));
+      else TRY(x_adj(h, xs, q, z0, zc, integ));
+      TRY(fwd_y(h, h->p2, h->p1t, 3, q, z0, zc, kernel_sync(h) ? XS_A : XS_NONE, true, ch, eA));
     }
+#if !defined(SMO_EMUL)
+    if (two) { CUDA_TRY(cudaEventRecord(h->ev_join, h->aux_stream)); CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
+#endif
     return 0;
   }
   // first half of a forward step only: x-spectra of the state whose z-padded form sits in p1t
@@ -912,9 +1051,9 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
     const unsigned long long a0 = h->epochA, b0 = h->epochB;
     const long long l0 = g_launches.load();
     en->ev0 = h->ev_used;
-    h->capturing = 1; h->cap_a0 = a0; h->cap_b0 = b0;
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(gc->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = 1; h->cap_a0 = a0; h->cap_b0 = b0;
     const int rc = body(gc->stream);
     const cudaError_t ce = cudaStreamEndCapture(gc->stream, &graph);
     h->capturing = 0;
@@ -940,7 +1079,10 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
   return 0;
 #endif
 }
-static int graph_opts(const smo_kdyn* h) { return (h->prof_which << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16); }
+static int graph_opts(const smo_kdyn* h) {
+  return ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
+         (h->two_streams ? 16 : 0) | ((h->push_waves & 7) << 5) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
+}
 
 // ---- snapshot store ------------------------------------------------------------------------------------------------
 // Forward states are kept in the form the adjoint x pass consumes: their x-spectra on this rank's z-slab, [Nh][M][nz] per
@@ -987,7 +1129,8 @@ static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double R
   if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));     // every rank has left whatever used the pencil buffers before
   const FwdStep first = step(0), last = step(n_steps - 1);
   GraphKey key; key.kind = (tail_xs_only ? 3 : 1) + (integ ? 10 : 0); key.n = n_steps; key.opts = graph_opts(h); key.p0 = first.xs[0]; key.p1 = last.cout[0];
-  key.p2 = first.cin[0]; key.Rm = Rm; key.dt = dt;    // (everything else a step touches follows from these by construction)
+  key.p2 = first.cin[0]; key.Rm = Rm; key.dt = dt; key.hsh = 0;
+  for (int n = 0; n < n_steps; ++n) { const FwdStep b = step(n); key.hsh = hash_ptr(hash_ptr(hash_ptr(key.hsh, b.cin[0]), b.cout[0]), b.xs[0]); }
   return run_graphed(h, key, st, [&](rt_stream s) -> int {
     TRY(KdOps<M>::inv_z(h, first.cin, h->p1, 3, s, XS_B));
     if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, s));
@@ -997,7 +1140,7 @@ static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double R
       TRY(KdOps<M>::yxy(h, 0, b.xs, s, integ));
       if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, s));
       const bool more = n + 1 < n_steps;
-      TRY(KdOps<M>::zstep(h, 0, b.cin, b.cout, more, Rm, dt, s));
+      TRY(KdOps<M>::zstep(h, 0, b.cin, b.cout, more, Rm, dt, s, KdOps<M>::yxy_chunks(h, 0)));
       if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 3, s));
     }
     return 0;
@@ -1010,9 +1153,8 @@ static void pingpong(cplx* const* a, cplx* const* b, int n, FwdStep& f) {
 // cost "Integrated" (KD:655-669): J = dt * sum_{n=0}^{N} <B^n,B^n>.  The states 0..N-1 pass through the forward x pass, which
 // sums |B^n|^2 over its grid points into per-CTA partials (deterministic: fixed tile assignment, fixed-order sums); the final
 // state is added from its grid values.
-static int jparts_begin(smo_kdyn* h, int n_steps, rt_stream st) {
-  const size_t per_step = 4096;     // >= CTAs of one step's x passes (<= 8 resident CTAs/SM x SMs, all chunks)
-  const size_t need = (size_t)n_steps * per_step;
+template <int M> static int jparts_begin(smo_kdyn* h, int n_steps, rt_stream st) {
+  const size_t need = (size_t)n_steps * KdOps<M>::jparts_per_step(h);   // exactly the slots the x passes of this solve fill
   if (need > h->jparts_cap) {
     rt_free(h->jparts); h->jparts = nullptr; h->jparts_cap = 0;
 #if !defined(SMO_EMUL)
@@ -1021,8 +1163,8 @@ static int jparts_begin(smo_kdyn* h, int n_steps, rt_stream st) {
     TRY(rt_malloc((void**)&h->jparts, sizeof(double) * need));
     h->jparts_cap = need;
   }
-  h->jparts_used = 0;
-  return rt_memset(h->jparts, 0, sizeof(double) * h->jparts_cap, st);
+  h->jparts_used = 0; h->jparts_need = need;
+  return rt_memset(h->jparts, 0, sizeof(double) * need, st);
 }
 // *J_host = J_final_term_host * dt + dt * scale * sum(partials)
 static int jparts_finish(smo_kdyn* h, size_t used, double dt, double scale, double* J_host, rt_stream st) {
@@ -1039,12 +1181,11 @@ template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const doub
                                        void* snaps, double* J_host, int flags, rt_stream st) {
   const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   TRY(kd_set_U<M>(h, U, st));
-  if (integ) TRY(jparts_begin(h, n_iters, st));
+  if (integ) TRY(jparts_begin<M>(h, n_iters, st));
   TRY(KdOps<M>::to_coef(h, B0, h->G, st));
   auto step = [&](int n) { FwdStep f; pingpong(h->G, h->NU, n, f); snap_xs(h, snaps, n, f.xs); return f; };
   // n_iters steps + the x-spectra of the final state (slot n_iters: continuous adjoint, and the cost below)
   TRY((kd_forward_loop<M>(h, n_iters + 1, true, Rm, dt, step, st, integ)));
-  const size_t jused = h->jparts_used;   // (a graph replay does not advance the host-side counter: recompute it below)
   const FwdStep fin = step(n_iters);
   cplx* sf[3];
   snap_final(h, snaps, n_iters, sf);
@@ -1055,8 +1196,8 @@ template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const doub
   const double scale = 1.0 / ((double)M * M * M);
   prof_collect(h, st);
   TRY(smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st));
-  (void)jused;
-  return integ ? jparts_finish(h, h->jparts_cap, dt, scale, J_host, st) : 0;
+  TRY(kd_check_err(h, "forward solve"));
+  return integ ? jparts_finish(h, h->jparts_need, dt, scale, J_host, st) : 0;
 }
 template <int M> static int kd_prep(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                                     double* out, rt_stream st) {
@@ -1076,7 +1217,8 @@ static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn
   if (count <= 0) return 0;
   const bool ks = kernel_sync(h);
   if (ks) TRY(a2a(h, h->p1, h->p1t, 3, st));
-  GraphKey key; key.kind = integ ? 12 : 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0).p[0]; key.p1 = state(count - 1).p[0]; key.p2 = nullptr; key.Rm = Rm; key.dt = dt;
+  GraphKey key; key.kind = integ ? 12 : 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0).p[0]; key.p1 = state(count - 1).p[0]; key.p2 = nullptr; key.Rm = Rm; key.dt = dt; key.hsh = 0;
+  for (int i = 0; i < count; ++i) key.hsh = hash_ptr(key.hsh, state(i).p[0]);
   return run_graphed(h, key, st, [&](rt_stream q) -> int {
     TRY(KdOps<M>::inv_z(h, h->W, h->p1, 3, q, XS_B));
     if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, q));
@@ -1085,7 +1227,7 @@ static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn
       TRY(KdOps<M>::yxy(h, 1, bf.p, q, integ));
       if (!ks) TRY(a2a(h, h->p1t, h->p1, 3, q));
       const bool more = i + 1 < count;
-      TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more, Rm, dt, q));
+      TRY(KdOps<M>::zstep(h, 1, nullptr, nullptr, more, Rm, dt, q, KdOps<M>::yxy_chunks(h, 1)));
       if (more && !ks) TRY(a2a(h, h->p1, h->p1t, 3, q));
     }
     return 0;
@@ -1130,7 +1272,7 @@ template <int M> static int kd_forward_ckpt(smo_kdyn* h, const double* B0, const
                                             int every, void* ck, double* J_host, int flags, rt_stream st) {
   const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   TRY(kd_set_U<M>(h, U, st));
-  if (integ) TRY(jparts_begin(h, n_iters, st));
+  if (integ) TRY(jparts_begin<M>(h, n_iters, st));
   cplx* s0[3];
   snap_ptrs(h, ck, 0, s0);
   TRY(KdOps<M>::to_coef(h, B0, s0, st));
@@ -1145,7 +1287,8 @@ template <int M> static int kd_forward_ckpt(smo_kdyn* h, const double* B0, const
   const double scale = 1.0 / ((double)M * M * M);
   prof_collect(h, st);
   TRY(smo_vec_dot(h->gwork, h->gwork, (long long)(3 * h->gsize), scale, J_host, h->vwork, (void*)st));
-  return integ ? jparts_finish(h, h->jparts_cap, dt, scale, J_host, st) : 0;
+  TRY(kd_check_err(h, "forward solve"));
+  return integ ? jparts_finish(h, h->jparts_need, dt, scale, J_host, st) : 0;
 }
 template <int M> static int kd_adjoint_ckpt(smo_kdyn* h, double Rm, double dt, int n_iters, int every, const void* ckc, void* seg,
                                             double* gB, double* gU, int flags, rt_stream st) {
@@ -1226,10 +1369,14 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->comm = comm;
   h->have_U = false;
   h->prof_which = 0; h->prof_ms = 0; h->prof_n = 0; h->use_graph = 0;
-  h->jparts = nullptr; h->jparts_cap = 0; h->jparts_used = 0;
+  h->jparts = nullptr; h->jparts_cap = 0; h->jparts_used = 0; h->jparts_need = 0;
   h->graphs = nullptr; h->capturing = 0; h->cap_a0 = h->cap_b0 = 0; h->epoch_dev = nullptr;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
   h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0; h->l2_hints = 1;
+  h->push_waves = 1; h->two_streams = 0; h->err_host = nullptr; h->err_dev = nullptr;
+#if !defined(SMO_EMUL)
+  h->aux_stream = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
+#endif
   for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < MAXP; ++s2) { h->peer_p1[f][s2] = h->peer_p1t[f][s2] = nullptr; }
   for (int s2 = 0; s2 < MAXP; ++s2) h->peer_flags[s2] = nullptr;
   h->chunks_fwd = h->chunks_adj = 1;    // off by default (measured slower at 128^3: the passes are not HBM-bound enough to gain)
@@ -1283,6 +1430,8 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
     }
   }
   rt_free(h->flags); rt_free(h->counters); rt_free(h->epoch_dev);
+  if (h->err_host) cudaFreeHost(h->err_host);
+  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
   if (h->graphs) {
     for (GraphEntry& e : h->graphs->e) if (e.exec) cudaGraphExecDestroy(e.exec);
     cudaStreamDestroy(h->graphs->stream); cudaEventDestroy(h->graphs->ev0); cudaEventDestroy(h->graphs->ev1);
@@ -1306,6 +1455,7 @@ extern "C" size_t smo_kdyn_segment_bytes(const smo_kdyn_t* h, int every) {
 }
 static int kd_args(smo_kdyn* h, double Rm, double dt, int n_iters, int flags, const char* who) {
   if (!h) return fail(SMO_E_ARG, "%s: null handle", who);
+  TRY(kd_check_err(h, who));
   if (!(Rm > 0) || !(dt > 0) || n_iters < 0) return fail(SMO_E_ARG, "%s: bad Rm/dt/n_iters", who);
   (void)flags;
   return 0;
@@ -1390,8 +1540,11 @@ extern "C" int smo_kdyn_peer_export(smo_kdyn_t* h, void* out) {
   if (h->nranks < 2) return fail(SMO_E_ARG, "smo_kdyn_peer_export: single-rank handle");
   if (h->nranks > MAXP) return fail(SMO_E_UNSUPPORTED, "peer transposes support at most %d ranks", MAXP);
   if (!h->flags) {
-    TRY(rt_malloc((void**)&h->flags, sizeof(unsigned long long) * 3 * MAXP));
-    TRY(rt_malloc((void**)&h->counters, sizeof(unsigned int) * 4));
+    TRY(rt_malloc((void**)&h->flags, sizeof(unsigned long long) * NFLAGW));
+    TRY(rt_malloc((void**)&h->counters, sizeof(unsigned int) * 3 * MAXCH));
+    CUDA_TRY(cudaHostAlloc((void**)&h->err_host, sizeof(unsigned int), cudaHostAllocMapped));
+    *h->err_host = 0u;
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&h->err_dev, h->err_host, 0));
     CUDA_TRY(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t* hd = (cudaIpcMemHandle_t*)out;
@@ -1444,6 +1597,8 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
     case SMO_OPT_KERNEL_SYNC: h->inkernel_sync = value ? 1 : 0; return 0;
     case SMO_OPT_PEER_PULL: h->peer_pull = value ? 1 : 0; return 0;
     case SMO_OPT_L2_HINTS: h->l2_hints = value ? 1 : 0; return 0;
+    case SMO_OPT_PUSH_WAVES: h->push_waves = value < 1 ? 1 : value; return 0;
+    case SMO_OPT_TWO_STREAMS: h->two_streams = value ? 1 : 0; return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic
       for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) { h->peer_p1[f][s2] = h->p1[f]; h->peer_p1t[f][s2] = h->p1t[f]; }
       return 0;

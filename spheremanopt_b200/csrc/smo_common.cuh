@@ -127,16 +127,59 @@ template <int N> SMO_HD void cp_async_wait() {
 // Epochs are `*base + offset` when `base` is set (launches replayed from a CUDA graph: the offsets are baked into the
 // graph, the base is bumped before every replay), else plain values.
 struct XSync {
-  const unsigned long long* wait_flags;   // local flag words, one per source rank; nullptr: no wait
+  const unsigned long long* wait_flags;   // local flag words (wait_n of them: source ranks x chunks); nullptr: no wait
   const unsigned long long* wait_base;
   unsigned long long wait_epoch;
-  int wait_n;
+  int wait_n, wait_per;                   // thread t < wait_n polls word (t / wait_per) * MAXP + t % wait_per
   int sig_n, sig_rank, sig_sys;           // sig_n = 0: no signal
   const unsigned long long* sig_base;
   unsigned long long sig_epoch;
-  unsigned long long* sig_flags[MAXP];    // the peers' flag arrays
+  unsigned long long* sig_flags[MAXP];    // the peers' flag words of this (buffer, chunk): word [sig_rank] is this rank's
   unsigned int* counter;                  // local: CTAs of this launch that have finished
+  unsigned int* err;                      // host-mapped word: set to 1 when a wait gave up (a peer died): results are invalid
 };
+// Flag loads / stores of the hand-shake.  The waiter's load is an acquire at system scope (everything the peer stored
+// before its release-ordered flag store is visible to the loads that follow); the signaller's last CTA orders the whole
+// launch's stores with a system-wide fence before it publishes.  SMO_XSYNC_RELAXED restores the round-1 fast path (plain
+// volatile accesses, device-scope fence in the last CTA) for A/B timing.
+SMO_HD unsigned long long xs_load_flag(const unsigned long long* f) {
+#if defined(__CUDA_ARCH__) && !defined(SMO_XSYNC_RELAXED)
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+  return v;
+#else
+  return *(const volatile unsigned long long*)f;
+#endif
+}
+SMO_HD void xs_store_flag(unsigned long long* f, unsigned long long v) {
+#if defined(__CUDA_ARCH__) && !defined(SMO_XSYNC_RELAXED)
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+#else
+  *(volatile unsigned long long*)f = v;
+#endif
+}
+#ifndef SMO_XSYNC_TIMEOUT_CYCLES
+#define SMO_XSYNC_TIMEOUT_CYCLES 20000000000ll   // ~10 s at 1.9 GHz: far beyond any legitimate wait inside a time loop
+#endif
+// bounded spin: returns false (and raises the error word) if the flag did not reach `want` in time
+SMO_HD bool xs_spin(const unsigned long long* f, unsigned long long want, unsigned int* err) {
+#if defined(__CUDA_ARCH__)
+  if (xs_load_flag(f) >= want) return true;
+  const long long t0 = clock64();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 256; ++i)
+      if (xs_load_flag(f) >= want) return true;
+    if (clock64() - t0 > SMO_XSYNC_TIMEOUT_CYCLES) {
+      if (err) *(volatile unsigned int*)err = 1u;
+      return false;
+    }
+  }
+#else
+  (void)f; (void)want; (void)err;
+  return true;
+#endif
+}
 template <class K, class = void> struct has_xsync { static constexpr bool value = false; };
 template <class K> struct has_xsync<K, decltype((void)((typename K::Params*)nullptr)->xs)> { static constexpr bool value = true; };
 
@@ -201,9 +244,8 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
   if constexpr (has_xsync<K>::value) {
     if (p.xs.wait_flags != nullptr) {
       if ((int)threadIdx.x < p.xs.wait_n) {
-        const volatile unsigned long long* f = p.xs.wait_flags + threadIdx.x;
         const unsigned long long want = p.xs.wait_epoch + (p.xs.wait_base ? *p.xs.wait_base : 0ull);
-        while (*f < want) { /* spin: the peer's kernel runs on another GPU */ }
+        xs_spin(p.xs.wait_flags + ((int)threadIdx.x / p.xs.wait_per) * MAXP + (int)threadIdx.x % p.xs.wait_per, want, p.xs.err);   // the peer's kernel runs on another GPU
       }
       __syncthreads();
     }
@@ -228,14 +270,20 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
     if (p.xs.sig_n > 0) {
       __syncthreads();
       if (threadIdx.x == 0) {
+        // the peers read (pull) or received (push) this launch's results: both need the stores ordered system-wide
+#if defined(SMO_XSYNC_RELAXED)
         if (p.xs.sig_sys) __threadfence_system(); else __threadfence();
+#else
+        __threadfence_system();
+#endif
         const unsigned int old = atomicAdd(p.xs.counter, 1u);
         if (old == gridDim.x - 1) {
           *p.xs.counter = 0u;   // ready for the next launch
+#if defined(SMO_XSYNC_RELAXED)
           __threadfence();
+#endif
           const unsigned long long val = p.xs.sig_epoch + (p.xs.sig_base ? *p.xs.sig_base : 0ull);
-          for (int s = 0; s < p.xs.sig_n; ++s)
-            *((volatile unsigned long long*)(p.xs.sig_flags[s] + p.xs.sig_rank)) = val;
+          for (int s = 0; s < p.xs.sig_n; ++s) xs_store_flag(p.xs.sig_flags[s] + p.xs.sig_rank, val);
         }
       }
     }

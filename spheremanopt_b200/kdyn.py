@@ -21,8 +21,10 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, sideout
 from .devvec import DevVec, VecOps, _stream_ptr, fingerprint
+
+SIDE_OUTPUTS = False   # True (or SMO_SIDE_OUTPUTS=1): write the reference's CheckPoints / scalar_data handlers (sideout.py)
 
 
 def _dist():
@@ -137,6 +139,15 @@ class Domain:
             s += p
         return s
 
+    def all_agree(self, flag, op):
+        """a yes/no decision every rank must take identically: MIN ("all say yes") or MAX ("any says yes") over the ranks"""
+        if self.nranks == 1:
+            return bool(flag)
+        dist = _dist()
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN if op == "min" else dist.ReduceOp.MAX)
+        return bool(int(t.item()))
+
     def __del__(self):
         try:
             if getattr(self, "h", None):
@@ -207,7 +218,9 @@ def GEN_BUFFER(Npts, domain, N_SUB_ITERS, checkpoint_every=None):
         need = domain.lib.smo_kdyn_snapshot_bytes(domain.h, int(N_SUB_ITERS))
         with torch.cuda.device(domain.device):
             free, _ = torch.cuda.mem_get_info()
-        checkpoint_every = 0 if need < 0.8 * free else int(np.ceil(np.sqrt(max(int(N_SUB_ITERS), 1))))
+        # every rank must take the same branch (the two stores issue different kernel / hand-shake sequences): MIN of "fits"
+        fits = domain.all_agree(need < 0.8 * free, "min")
+        checkpoint_every = 0 if fits else int(np.ceil(np.sqrt(max(int(N_SUB_ITERS), 1))))
     if checkpoint_every and checkpoint_every > 0:
         return CheckpointStore(domain, N_SUB_ITERS, checkpoint_every)
     return SnapshotStore(domain, N_SUB_ITERS)
@@ -272,14 +285,42 @@ def FWD_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost
                                                                 _flags(Cost_function, "Discrete"), _stream_ptr()))
     X_FWD_DICT.valid = True
     X_FWD_DICT.tag = (fingerprint(X0[0]), fingerprint(X0[1]), float(Rm), float(dt), int(N_ITERS), Cost_function)
+    if sideout.enabled(SIDE_OUTPUTS):
+        _side_outputs(domain, Bt, Ut, dt, int(N_ITERS), X_FWD_DICT)
     return (-1.) * domain.allreduce_sum(J.value)
+
+
+def _side_outputs(domain, Bt, Ut, dt, n_iters, store):
+    """KD:606-613: CheckPoints (iterations 0 and N: A, B, C and the projected velocity on the 3/2 grid) and scalar_data
+    ("Magnetic energy" every 20 iterations; a CheckpointStore only holds the states its spacing keeps)"""
+    if isinstance(store, CheckpointStore):
+        have = [n for n in range(0, n_iters + 1, 20) if n % store.every == 0 or n == n_iters]
+        coef_of = lambda n: store.buf.view(-1, 3 * domain.csize)[n // store.every if n != n_iters else -1].clone()
+    else:
+        have = list(range(0, n_iters + 1, 20))
+
+        def coef_of(n):
+            c = torch.zeros(3 * domain.csize, dtype=torch.complex128, device=domain.device)
+            with torch.cuda.device(domain.device):
+                _cabi.check(domain.lib, domain.lib.smo_kdyn_snapshot_coef(domain.h, store.ptr(), n_iters, n, c.data_ptr(), _stream_ptr()))
+            return c
+    en = []
+    for n in have:
+        g = to_grid(domain, coef_of(n))
+        en.append(Inner_Prod_3(DevVec(g), DevVec(g), domain))
+    last = to_grid(domain, coef_of(n_iters))
+    Up = to_grid(domain, to_coef(domain, Ut).reshape(-1))          # parameter fields are projected on the retained modes [D2-8]
+    Bf, Bl, Uh = domain.host_from_slab(Bt), domain.host_from_slab(last), domain.host_from_slab(Up)
+    if domain.rank == 0:
+        sideout.kdyn_outputs(domain, have, en, Bf, Bl, Uh, dt, n_iters)
 
 
 def ADJ_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost_function="Final", Adjoint_type="Discrete"):
     """KD:766-1004.  Returns [dJ/dB0, dJ/dU] in the layout/type of X0."""
     if not X_FWD_DICT.valid:
         raise RuntimeError("ADJ_Solve_IVP_Lin needs the snapshots of a preceding FWD_Solve_IVP_Lin (KD:955-957)")
-    if getattr(X_FWD_DICT, "tag", None) != (fingerprint(X0[0]), fingerprint(X0[1]), float(Rm), float(dt), int(N_ITERS), Cost_function):
+    stale = getattr(X_FWD_DICT, "tag", None) != (fingerprint(X0[0]), fingerprint(X0[1]), float(Rm), float(dt), int(N_ITERS), Cost_function)
+    if domain.all_agree(stale, "max"):    # (sharded vectors: one rank's slab may differ while another's does not - MAX of "stale")
         # the store was written for another X or other parameters (never happens in the reference optimiser): refill it
         FWD_Solve_IVP_Lin(X0, domain, Rm, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, Cost_function, Adjoint_type)
     gB = torch.empty(3 * domain.gsize, dtype=torch.float64, device=domain.device)
@@ -377,5 +418,5 @@ def Generate_IC(Npts, X=(0., 2. * np.pi), M_0=1.0, U_Noise=False, Rm=1.0, dt=5e-
 
 
 def File_Manips(k):
-    """KD:1006-1021 copies dedalus HDF5 outputs that this implementation does not write (out of scope, SURVEY 8(f) #2)."""
-    return None
+    """KD:1006-1021: keeps scalar_data / CheckPoints of optimiser iteration k (needs SIDE_OUTPUTS; .npz, and .h5 with h5py)."""
+    return sideout.file_manips(k)

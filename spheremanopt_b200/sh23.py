@@ -22,10 +22,11 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _cabi
+from . import _cabi, sideout
 from .devvec import DevVec, VecOps, _stream_ptr, fingerprint
 
 PARAM_A = -0.3   # SH:309
+SIDE_OUTPUTS = False   # True (or SMO_SIDE_OUTPUTS=1): write the reference's CheckPoints / scalar_data handlers (sideout.py)
 
 
 class Domain:
@@ -149,6 +150,8 @@ def FWD_Solve_IVP_Lin(X_k, domain, dt, N_ITERS, N_SUB_ITERS, X_FWD_DICT, filenam
     J = forward_batch(X_k[0], domain, dt, N_ITERS, X_FWD_DICT)
     X_FWD_DICT.tag = (fingerprint(X_k[0]), float(dt), int(N_ITERS))
     Jh = J.cpu().numpy()
+    if Jh.size == 1 and sideout.enabled(SIDE_OUTPUTS):      # SH:478-483 (one problem only, like the reference)
+        sideout.sh23_outputs(domain, X_FWD_DICT['A_fwd'], dt, N_ITERS)
     return (-1.) * float(Jh[0]) if Jh.size == 1 else (-1.) * Jh
 
 
@@ -210,5 +213,5 @@ def Generate_IC(E_0=1.0, Npts=256, X=(0., 12. * np.pi), device="cuda:0", as_devv
 
 
 def File_Manips(k):
-    """SH:731-746 copies dedalus HDF5 outputs that this implementation does not write (out of scope, SURVEY 8(f) #2)."""
-    return None
+    """SH:731-746: keeps scalar_data / CheckPoints of optimiser iteration k (needs SIDE_OUTPUTS; .npz, and .h5 with h5py)."""
+    return sideout.file_manips(k)

@@ -28,13 +28,22 @@ def pytest_collection_modifyitems(config, items):
             it.add_marker(skip)
 
 
+def reference_dir():
+    """where the UNMODIFIED reference optimiser files can be imported from: $SMO_REFERENCE_DIR, /root/reference (build
+    container) or baseline/_ref (staged by tools/stage_reference.py; travels to the GPU box, git-ignored)"""
+    for d in (os.environ.get("SMO_REFERENCE_DIR"), REFERENCE, os.path.join(ROOT, "baseline", "_ref")):
+        if d and os.path.isfile(os.path.join(d, "Sphere_Grad_Descent.py")) and os.path.isfile(os.path.join(d, "TestGrad.py")):
+            return d
+    return None
+
+
 @pytest.fixture(scope="session")
 def refopt():
-    """The UNMODIFIED reference optimiser / gradient test, imported from /root/reference when it is there
-    (build container only).  Returns (Sphere_Grad_Descent, TestGrad) or skips."""
-    if not os.path.isdir(REFERENCE):
-        pytest.skip("/root/reference not present on this box")
-    for p in (REFSTUBS, REFERENCE):
+    """The UNMODIFIED reference optimiser / gradient test.  Returns (Sphere_Grad_Descent, TestGrad) or skips."""
+    d = reference_dir()
+    if d is None:
+        pytest.skip("reference optimiser files not present (no /root/reference, no baseline/_ref)")
+    for p in (REFSTUBS, d):
         if p not in sys.path:
             sys.path.insert(0, p)
     import Sphere_Grad_Descent as SGD

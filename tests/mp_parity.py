@@ -27,7 +27,7 @@ def main():
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cases = [(32, 6)] if world > 2 else [(16, 5), (32, 6)]
+    cases = [(32, 6)] if world > 2 else [(16, 5), (32, 6), (64, 3)]      # (64: nz = 48 per rank at P = 2 -> chunked variants run)
     worst = 0.0
     for Npts, nit in cases:
         od = okd.domain_kdyn(Npts)
@@ -38,12 +38,22 @@ def main():
         D = okd.GEN_BUFFER(Npts, od, nit)
         fo = okd.FWD_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
         go = okd.ADJ_Solve_IVP_Lin([B0, U], od, Rm, dt, nit, nit, D)
-        # (peer memory, in-kernel hand-shakes, graph replay, pull transposes)
-        for peer, ksync, fused, pull in ((True, 1, 1, 1), (True, 0, 0, 1), (True, 1, 0, 0), (True, 1, 1, 0), (True, 0, 0, 0), (False, 0, 0, 0)):
+        # (peer memory, in-kernel hand-shakes, graph replay, pull transposes, z chunks of the y-x-y section, two streams,
+        #  work items per CTA of the pushing kernels, checkpoint spacing)
+        variants = ((True, 1, 1, 1, 1, 0, 1, 0), (True, 0, 0, 1, 1, 0, 1, 0), (True, 1, 0, 0, 1, 0, 1, 0), (True, 1, 1, 0, 1, 0, 1, 0),
+                    (True, 0, 0, 0, 1, 0, 1, 0), (False, 0, 0, 0, 1, 0, 1, 0),
+                    (True, 1, 1, 0, 2, 1, 2, 0), (True, 1, 0, 0, 2, 1, 1, 0), (True, 1, 1, 0, 2, 0, 3, 0), (True, 1, 1, 1, 2, 1, 1, 0),
+                    (True, 1, 1, 0, 1, 0, 1, 4), (True, 1, 1, 0, 2, 1, 2, 3), (False, 0, 0, 0, 1, 0, 1, 4))
+        for peer, ksync, fused, pull, chunks, two, waves, every in variants:
+            if chunks > 1 and ((3 * Npts // 2) // world) % (8 * chunks):
+                continue     # (a z chunk must hold whole tiles of the y passes)
             dom = kdyn.Domain(Npts, device="cuda:%d" % local, peer_memory=peer)
             dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_KERNEL_SYNC, ksync)
             dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_PEER_PULL, pull)
-            store = kdyn.GEN_BUFFER(Npts, dom, nit)
+            dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_TWO_STREAMS, two)
+            dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_PUSH_WAVES, waves)
+            dom.lib.smo_kdyn_set_chunks(dom.h, chunks, chunks)
+            store = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=every)
             if peer and ksync and fused:
                 dom.lib.smo_kdyn_use_graph(dom.h, 1)     # graph replay with device-side epoch bases (3rd call onwards)
             for rep in range(4):     # repeatedly: epochs / counters / graph replays must survive repeated calls
@@ -59,7 +69,8 @@ def main():
             e.append(abs(ip - okd.Inner_Prod_3(go[0], B0, od)) / abs(okd.Inner_Prod_3(go[0], B0, od)))
             worst = max(worst, max(e))
             if rank == 0:
-                print("P=%d N=%d peer=%d ksync=%d graph=%d pull=%d: max rel.err %.2e" % (world, Npts, peer, ksync, fused, pull, max(e)), flush=True)
+                print("P=%d N=%d peer=%d ksync=%d graph=%d pull=%d chunks=%d two_streams=%d waves=%d ckpt_every=%d: max rel.err %.2e"
+                      % (world, Npts, peer, ksync, fused, pull, chunks, two, waves, every, max(e)), flush=True)
             del dom, store
     ok = torch.tensor([1 if worst <= TOL else 0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)

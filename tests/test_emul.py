@@ -225,3 +225,29 @@ def test_vector_kernels_emulated(L):
     for m in (1, 511, 8193):
         emul.check(L.smo_vec_dot(emul.ptr(x), emul.ptr(d), m, 1.0, C.byref(out), emul.ptr(work), None))
         assert abs(out.value - float(np.dot(x[:m], d[:m]))) <= 1e-12 * m
+
+
+def test_vector_kernels_alignment_paths_and_checksum_emulated(L):
+    """128-bit (pair) path vs the scalar path (operands offset by one double), odd lengths; the 64-bit checksum"""
+    r = np.random.RandomState(1)
+    for n in (2, 3, 8192, 8193, 20001):
+        buf = [r.standard_normal(n + 2) for _ in range(3)]
+        work = np.zeros(L.smo_vec_work_bytes(n) // 8 + 1)
+        for off in (0, 1):       # off = 1: 8-byte aligned only -> scalar path
+            x, d, y = (b[off:off + n] for b in buf)
+            out = C.c_double()
+            emul.check(L.smo_vec_dot(emul.ptr(x), emul.ptr(d), n, 1.0, C.byref(out), emul.ptr(work), None))
+            assert abs(out.value - float(np.dot(x, d))) <= 1e-12 * n
+            emul.check(L.smo_vec_axpby(0.3, emul.ptr(x), -2.0, emul.ptr(d), emul.ptr(y), n, None))
+            assert relerr(y, 0.3 * x - 2.0 * d) <= 1e-15
+            emul.check(L.smo_vec_project(emul.ptr(x), emul.ptr(d), emul.ptr(y), n, emul.ptr(work), None))
+            assert relerr(y, d - (np.dot(x, d) / np.dot(x, x)) * x) <= 1e-12
+            emul.check(L.smo_vec_retract(emul.ptr(x), 0.7, emul.ptr(d), 2.5, 0.5, emul.ptr(y), n, emul.ptr(work), None))
+            f = x + 0.7 * d
+            assert relerr(y, f * np.sqrt(2.5 / (0.5 * np.dot(f, f)))) <= 1e-12
+        x = np.ascontiguousarray(buf[0][:n])
+        h = C.c_ulonglong()
+        emul.check(L.smo_vec_checksum(emul.ptr(x), n, C.byref(h), emul.ptr(work), None))
+        bits = x.view(np.uint64)
+        with np.errstate(over="ignore"):
+            assert h.value == int((bits * (2 * np.arange(n, dtype=np.uint64) + np.uint64(1))).sum(dtype=np.uint64))

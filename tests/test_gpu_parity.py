@@ -375,3 +375,66 @@ def test_errors_are_loud():
     store = sh23.GEN_BUFFER(dom, 5)
     with pytest.raises(RuntimeError):
         sh23.ADJ_Solve_IVP_Lin([np.zeros(128)], dom, 0.1, 5, 5, store)   # Grad_f before f
+
+
+def test_kdyn_graph_cache_distinguishes_checkpoint_spacing():
+    """two CheckpointStores with the same N_ITERS, the same slot count (N=12: every=4 and every=5 both give 4 slots)
+    and - through torch's caching allocator - the same addresses must not replay each other's CUDA graph"""
+    import torch
+    from spheremanopt_b200 import kdyn
+    Npts, nit = 24, 12
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    full = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=0)
+    f0 = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, full)
+    g0 = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, full)
+    del full
+    dom.lib.smo_kdyn_use_graph(dom.h, 1)
+    ptrs = []
+    for every in (4, 5, 4):
+        ck = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=every)
+        ptrs.append(ck.ptr())
+        for rep in range(3):     # eager, capture, replay
+            fc = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, ck)
+            gc = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, ck)
+            assert fc == f0 and np.array_equal(gc[0], g0[0]) and np.array_equal(gc[1], g0[1]), (every, rep)
+        del ck
+        torch.cuda.synchronize()
+    print("checkpoint buffers reused the same address:", len(set(ptrs)) < len(ptrs))
+
+
+def test_two_domains_on_two_devices_in_one_process():
+    """launch configuration (dynamic shared-memory opt-in, occupancy) is per device"""
+    import torch
+    from spheremanopt_b200 import kdyn
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    od = okd.domain_kdyn(24)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        dom = kdyn.Domain(24, device=dev, distributed=False)
+        st = kdyn.GEN_BUFFER(24, dom, 5, checkpoint_every=0)
+        f = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, 5, 5, st)
+        g = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, 5, 5, st)
+        res.append((f, g[0], g[1]))
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
+def test_fingerprint_sees_single_entry_changes():
+    """the identity check of the snapshot store's X is a checksum of EVERY entry of a device vector (round 1 sampled 5)"""
+    import torch
+    from spheremanopt_b200.devvec import DevVec, fingerprint
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(3 * 36 ** 3, dtype=torch.float64, generator=g).cuda()
+    fp = fingerprint(DevVec(x))
+    bits = x.cpu().numpy().view(np.uint64)
+    with np.errstate(over="ignore"):
+        want = int((bits * (2 * np.arange(bits.size, dtype=np.uint64) + np.uint64(1))).sum(dtype=np.uint64))
+    assert fp == (x.numel(), want)
+    for idx in (1, 777, x.numel() - 2):
+        y = x.clone(); y[idx] = y[idx] * (1 + 1e-15) + 1e-300
+        assert fingerprint(DevVec(y)) != fp
+    perm = x.clone(); perm[[5, 6]] = perm[[6, 5]]
+    assert fingerprint(DevVec(perm)) != fp      # position sensitive
