@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "libsmo_b200.so")
 SOURCES = ["smo_api.cu"]
-HEADERS = ["smo_common.cuh", "codelets.cuh", "fft_core.cuh", "fft_pass.cuh", "xpass.cuh", "kd_epilogue.cuh", "zstep.cuh",
+HEADERS = ["smo_common.cuh", "codelets.cuh", "fft_core.cuh", "fft_pass.cuh", "xpass.cuh", "xpass_half.cuh", "kd_epilogue.cuh", "zstep.cuh",
            "sh23.cuh", "reduce.cuh", os.path.join("..", "..", "include", "smo_b200.h")]
 
 

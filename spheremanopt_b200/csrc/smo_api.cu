@@ -8,6 +8,7 @@
 #include "../../include/smo_b200.h"
 #include "fft_pass.cuh"
 #include "xpass.cuh"
+#include "xpass_half.cuh"
 #include "kd_epilogue.cuh"
 #include "zstep.cuh"
 #include "sh23.cuh"
@@ -714,8 +715,20 @@ static void xs_wait(smo_kdyn* h, XSync& xs, int which, int nch = 1) {
 }
 
 // ---- pass launchers ---------------------------------------------------------------------------------------
+// which fused x pass serves grid length M: the pair-packed XFused (two real columns per complex FFT of length M), or - where M
+// has no 16-thread factorisation (M = 384) - the half-length XFusedH (one real column per complex FFT of length M/2)
+#if defined(SMO_TEST_HALFX)   // test-only: exercises the half-length code paths at a small size (M = 96: H = 48 = 8 x 6)
+template <int M> struct UseHalfX { static constexpr bool value = (M == 384) || (M == 96); };
+#else
+template <int M> struct UseHalfX { static constexpr bool value = (M == 384); };
+#endif
+template <int M, int MODE, bool INTEG, bool HALF> struct XKernelOf { typedef XFused<typename FacOf<M>::type, MODE, INTEG> type; };
+template <int M, int MODE, bool INTEG> struct XKernelOf<M, MODE, INTEG, true> { typedef XFusedH<typename FacOf<M / 2>::type, MODE, INTEG> type; };
+
 template <int M> struct KdOps {
   typedef typename FacOf<M>::type F;
+  static constexpr bool HALFX = UseHalfX<M>::value;
+  template <int MODE, bool INTEG> using XK = typename XKernelOf<M, MODE, INTEG, HALFX>::type;
   static constexpr int TZ = SMO_TZ;    // lines per CTA, contiguous (z) passes
   static constexpr int TY = SMO_TY;    // lines per CTA, strided (y) passes
   static constexpr int TX = SMO_TX;    // columns per CTA, x passes with <= 3 fields
@@ -845,7 +858,7 @@ template <int M> struct KdOps {
   static size_t jparts_per_step(smo_kdyn* h) {
     const int nch = yxy_chunks(h, 0);
     XFParams p; xffill(p, h, 4, 0, nch > 1 ? h->nz / nch : -1);
-    return (size_t)nch * (size_t)grid_for<XFused<F, X_FWD, true>>(p.nwork);
+    return (size_t)nch * (size_t)grid_for<XK<X_FWD, true>>(p.nwork);
   }
   // forward: x-spectra of B (the snapshot slot or the work arrays) in, x-spectra of U x B out (work arrays)
   static int x_fwd(smo_kdyn* h, cplx* const* bp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
@@ -853,14 +866,14 @@ template <int M> struct KdOps {
     for (int f = 0; f < 3; ++f) { p.sin[f] = bp2[f]; p.sout[f] = h->p2[f]; }
     int rc;
     if (integ) {   // cost "Integrated": this launch's per-CTA sums of |B|^2 go to the next free slots of jparts
-      const int grid = grid_for<XFused<F, X_FWD, true>>(p.nwork);
+      const int grid = grid_for<XK<X_FWD, true>>(p.nwork);
       if (h->jparts_used + (size_t)grid > h->jparts_cap) return fail(SMO_E_STATE, "x_fwd: partial-sum buffer too small");
       p.jpart = h->jparts + h->jparts_used; h->jparts_used += (size_t)grid;
       prof_begin(h, PK_X, st);
-      rc = launch<XFused<F, X_FWD, true>>(p, st);
+      rc = launch<XK<X_FWD, true>>(p, st);
     } else {
       prof_begin(h, PK_X, st);
-      rc = launch<XFused<F, X_FWD>>(p, st);
+      rc = launch<XK<X_FWD, false>>(p, st);
     }
     prof_end(h, PK_X, st);
     return rc;
@@ -872,7 +885,7 @@ template <int M> struct KdOps {
     for (int c = 0; c < 3; ++c) p.sout[3 + c] = h->acc[c];    // (curl G) x B_f: summed over the sweep on the x-spectra
     p.accumulate = 1;
     prof_begin(h, PK_XA, st);
-    int rc = integ ? launch<XFused<F, X_ADJ, true>>(p, st) : launch<XFused<F, X_ADJ>>(p, st);
+    int rc = integ ? launch<XK<X_ADJ, true>>(p, st) : launch<XK<X_ADJ, false>>(p, st);
     prof_end(h, PK_XA, st);
     return rc;
   }
@@ -881,6 +894,7 @@ template <int M> struct KdOps {
     for (int c = 0; c < 3; ++c) p.in[c] = h->Ug[c];
     p.out = h->Ut; p.ncols = (long long)M * h->nz; p.M = M; p.nsteps = 1;
     p.nwork = (int)(M * ((p.ncols + UTile::THREADS - 1) / UTile::THREADS));
+    if (HALFX) return launch<UTileH>(p, st);
     return launch<UTile>(p, st);
   }
 

@@ -251,3 +251,28 @@ def test_vector_kernels_alignment_paths_and_checksum_emulated(L):
         bits = x.view(np.uint64)
         with np.errstate(over="ignore"):
             assert h.value == int((bits * (2 * np.arange(n, dtype=np.uint64) + np.uint64(1))).sum(dtype=np.uint64))
+
+
+def test_kdyn_half_length_x_pass_emulated():
+    """the half-length fused x pass of the 256^3 grid (xpass_half.cuh: one real column = one complex FFT of length M/2) at a
+    size the host emulation can afford: M = 96 served by XFusedH<Fac<8,6>> (test-only switch SMO_TEST_HALFX), both costs"""
+    LH = emul.lib_variant("halfx", ["SMO_TEST_HALFX"])
+    Npts, nit = 64, 2
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    chk = lambda rc: emul._cabi.check(LH, rc)
+    chk(LH.smo_kdyn_create(C.byref(h), Npts, od.L, 0, 1, None))
+    gsz = LH.smo_kdyn_grid_elems(h)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    for cost, flag in (("Final", 0), ("Integrated", 2)):
+        snaps = np.zeros(LH.smo_kdyn_snapshot_bytes(h, nit) // 16, dtype=complex)
+        J = C.c_double()
+        gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
+        chk(LH.smo_kdyn_forward(h, emul.ptr(B0), emul.ptr(U), 2.0, 1e-3, nit, emul.ptr(snaps), C.byref(J), flag, None))
+        chk(LH.smo_kdyn_adjoint(h, 2.0, 1e-3, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), flag, None))
+        fo = okd.FWD_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D, cost)
+        go = okd.ADJ_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D, cost)
+        assert abs(-J.value - fo) <= TOL * abs(fo)
+        assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    LH.smo_kdyn_destroy(h)
