@@ -153,6 +153,13 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* SMO_OPT_TWO_STREAMS: 1 = the z chunks of the y -> fused x -> y section (smo_kdyn_set_chunks) alternate between two CUDA
  * streams, so that one chunk's NVLink transfer and hand-shake overlap the other chunk's x pass; 0 (default) = one stream. */
 #define SMO_OPT_TWO_STREAMS 6
+/* SMO_OPT_GRID_ACC: 1 (default) = the fused adjoint x pass adds its (curl G) x B_f products to a running sum ON THE GRID (tile-major,
+ * read-modify-write straight from registers) and skips their r2c transform; one transform after the sweep replaces 3 of the 6
+ * forward FFTs of every adjoint step (KD:874-877 is linear in the products).  0 = running sum on the x-spectra. */
+#define SMO_OPT_GRID_ACC 7
+/* SMO_OPT_BULK_U: 1 (default) = the fused x passes fetch the velocity tile of a column tile (18 KB at 128^3, stored in HBM in its
+ * swizzled shared-memory order) with ONE TMA bulk copy (cp.async.bulk + mbarrier) instead of 16-byte cp.async copies. */
+#define SMO_OPT_BULK_U 8
 int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);

@@ -82,6 +82,8 @@ SMO_OPT_PEER_PULL = 3
 SMO_OPT_L2_HINTS = 4
 SMO_OPT_PUSH_WAVES = 5
 SMO_OPT_TWO_STREAMS = 6
+SMO_OPT_GRID_ACC = 7
+SMO_OPT_BULK_U = 8
 
 
 def bind(cdll):

@@ -533,6 +533,8 @@ struct smo_kdyn {
   int inkernel_sync; unsigned long long epochA, epochB; unsigned int* counters;
   int l2_hints;                 // 1: L2 residency hints on the pencil data of the time loops (single rank)
   int peer_pull;                // 0 (default, measured faster on 2 B200): producers push; 1: consumers pull from the peers' buffers
+  int bulk_u;                   // 1: the x passes fetch their velocity tile with one TMA bulk copy per tile
+  int grid_acc; double* accg;   // 1: the adjoint x pass sums (curl G) x B_f on the real grid (tile-major, 3*gsize doubles) instead of on the x-spectra
   int push_waves;               // pushing kernels run ~push_waves work items per CTA so that remote stores drain under compute
   int two_streams;              // 1: the z chunks of the y -> x -> y section alternate between two streams (transfers of one
                                 // chunk overlap the x pass of the next)
@@ -722,13 +724,13 @@ template <int M> struct UseHalfX { static constexpr bool value = (M == 384) || (
 #else
 template <int M> struct UseHalfX { static constexpr bool value = (M == 384); };
 #endif
-template <int M, int MODE, bool INTEG, bool HALF> struct XKernelOf { typedef XFused<typename FacOf<M>::type, MODE, INTEG> type; };
-template <int M, int MODE, bool INTEG> struct XKernelOf<M, MODE, INTEG, true> { typedef XFusedH<typename FacOf<M / 2>::type, MODE, INTEG> type; };
+template <int M, int MODE, bool INTEG, bool GACC, bool HALF> struct XKernelOf { typedef XFused<typename FacOf<M>::type, MODE, INTEG, GACC> type; };
+template <int M, int MODE, bool INTEG, bool GACC> struct XKernelOf<M, MODE, INTEG, GACC, true> { typedef XFusedH<typename FacOf<M / 2>::type, MODE, INTEG, GACC> type; };
 
 template <int M> struct KdOps {
   typedef typename FacOf<M>::type F;
   static constexpr bool HALFX = UseHalfX<M>::value;
-  template <int MODE, bool INTEG> using XK = typename XKernelOf<M, MODE, INTEG, HALFX>::type;
+  template <int MODE, bool INTEG, bool GACC = false> using XK = typename XKernelOf<M, MODE, INTEG, GACC, HALFX>::type;
   static constexpr int TZ = SMO_TZ;    // lines per CTA, contiguous (z) passes
   static constexpr int TY = SMO_TY;    // lines per CTA, strided (y) passes
   static constexpr int TX = SMO_TX;    // columns per CTA, x passes with <= 3 fields
@@ -847,7 +849,7 @@ template <int M> struct KdOps {
   }
   static void xffill(XFParams& p, smo_kdyn* h, int T, int z0, int nzc) {
     memset(&p, 0, sizeof p);
-    p.nsteps = 1; p.ncols = (long long)M * h->nz; p.Nh = h->Nh; p.tw = h->tw; p.scale = 1.0 / M; p.ut = h->Ut;
+    p.nsteps = 1; p.ncols = (long long)M * h->nz; p.Nh = h->Nh; p.tw = h->tw; p.scale = 1.0 / M; p.ut = h->Ut; p.bulk_u = h->bulk_u;
     if (nzc < 0) {   // all columns: tiles of T consecutive (y,z) columns, may straddle rows
       p.tiles_per_row = (int)(p.ncols / T); p.row_tiles = 0; p.tile0 = 0; p.nwork = p.tiles_per_row;
     } else {         // z range [z0, z0+nzc) of every row (needs nz, z0, nzc multiples of T)
@@ -882,10 +884,16 @@ template <int M> struct KdOps {
   static int x_adj(smo_kdyn* h, cplx* const* bfp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
     XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = h->p2[f]; p.sout[f] = h->p2[f]; p.sin[3 + f] = bfp2[f]; }
-    for (int c = 0; c < 3; ++c) p.sout[3 + c] = h->acc[c];    // (curl G) x B_f: summed over the sweep on the x-spectra
     p.accumulate = 1;
     prof_begin(h, PK_XA, st);
-    int rc = integ ? launch<XK<X_ADJ, true>>(p, st) : launch<XK<X_ADJ, false>>(p, st);
+    int rc;
+    if (h->grid_acc) {   // (curl G) x B_f: summed over the sweep on the real grid, transformed once afterwards (nu_finish)
+      p.gacc = h->accg;
+      rc = integ ? launch<XK<X_ADJ, true, true>>(p, st) : launch<XK<X_ADJ, false, true>>(p, st);
+    } else {             // ... summed on the x-spectra
+      for (int c = 0; c < 3; ++c) p.sout[3 + c] = h->acc[c];
+      rc = integ ? launch<XK<X_ADJ, true>>(p, st) : launch<XK<X_ADJ, false>>(p, st);
+    }
     prof_end(h, PK_XA, st);
     return rc;
   }
@@ -1012,6 +1020,10 @@ template <int M> struct KdOps {
   }
   // start of an adjoint sweep: the running sum of the (curl G) x B_f spectra is cleared
   static int acc_begin(smo_kdyn* h, rt_stream st) {
+    if (h->grid_acc) {
+      if (!h->accg) TRY(rt_malloc((void**)&h->accg, sizeof(double) * 3 * h->gsize));
+      return rt_memset(h->accg, 0, sizeof(double) * 3 * h->gsize, st);
+    }
     for (int c = 0; c < 3; ++c) {
       if (!h->acc[c]) TRY(rt_malloc((void**)&h->acc[c], sizeof(cplx) * h->p2size));
       TRY(rt_memset(h->acc[c], 0, sizeof(cplx) * h->p2size, st));
@@ -1020,8 +1032,18 @@ template <int M> struct KdOps {
   }
   // end of the sweep: nu^N = -dt P_k[ y/z transforms of the running sum ]   (once instead of every step)
   static int nu_finish(smo_kdyn* h, double Rm, double dt, rt_stream st) {
+    if (h->grid_acc) {   // tile-major running sum -> grid -> x-spectra (the one r2c transform the sweep skipped)
+      UTileParams u; memset(&u, 0, sizeof u);
+      for (int c = 0; c < 3; ++c) u.in[c] = h->gwork + (size_t)c * h->gsize;
+      u.out = h->accg; u.ncols = (long long)M * h->nz; u.M = M; u.nsteps = 1; u.half = HALFX ? 1 : 0;
+      u.nwork = (int)(M * ((u.ncols + UnTile::THREADS - 1) / UnTile::THREADS));
+      TRY(launch<UnTile>(u, st));
+      const double* g[3] = {h->gwork, h->gwork + h->gsize, h->gwork + 2 * h->gsize};
+      TRY(x_r2c(h, g, h->p2, st));
+    }
+    cplx* const* accx = h->grid_acc ? h->p2 : h->acc;
     if (h->peer_on) TRY(a2a(h, h->p1t, h->p1, 3, st));
-    TRY(fwd_y(h, h->acc, h->p1t, 3, st));
+    TRY(fwd_y(h, accx, h->p1t, 3, st));
     TRY(a2a(h, h->p1t, h->p1, 3, st));
     TRY(fwd_z(h, h->p1, h->cw, 3, st));
     EpiParams e; efill(e, h, Rm, dt, 0);
@@ -1095,7 +1117,7 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
 }
 static int graph_opts(const smo_kdyn* h) {
   return ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
-         (h->two_streams ? 16 : 0) | ((h->push_waves & 7) << 5) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
+         (h->two_streams ? 16 : 0) | ((h->push_waves & 3) << 5) | (h->grid_acc ? 128 : 0) | (h->bulk_u ? (1 << 28) : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
 }
 
 // ---- snapshot store ------------------------------------------------------------------------------------------------
@@ -1387,6 +1409,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->graphs = nullptr; h->capturing = 0; h->cap_a0 = h->cap_b0 = 0; h->epoch_dev = nullptr;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
   h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0; h->l2_hints = 1;
+  h->grid_acc = 1; h->accg = nullptr; h->bulk_u = 1;     // (r2e: adjoint x pass 221 -> 196 us at 128^3, 2.46 -> 2.04 ms at 256^3)
   h->push_waves = 1; h->two_streams = 0; h->err_host = nullptr; h->err_dev = nullptr;
 #if !defined(SMO_EMUL)
   h->aux_stream = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
@@ -1434,7 +1457,7 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
     rt_free(h->p1[f]); rt_free(h->p2[f]); rt_free(h->cw[f]);
   }
   for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); rt_free(h->acc[c]); }
-  rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut); rt_free(h->jparts);
+  rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut); rt_free(h->jparts); rt_free(h->accg);
 #if !defined(SMO_EMUL)
   if (h->peer_on) {
     for (int s = 0; s < h->nranks; ++s) {
@@ -1613,6 +1636,8 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
     case SMO_OPT_L2_HINTS: h->l2_hints = value ? 1 : 0; return 0;
     case SMO_OPT_PUSH_WAVES: h->push_waves = value < 1 ? 1 : value; return 0;
     case SMO_OPT_TWO_STREAMS: h->two_streams = value ? 1 : 0; return 0;
+    case SMO_OPT_GRID_ACC: h->grid_acc = value ? 1 : 0; return 0;
+    case SMO_OPT_BULK_U: h->bulk_u = value ? 1 : 0; return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic
       for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) { h->peer_p1[f][s2] = h->p1[f]; h->peer_p1t[f][s2] = h->p1t[f]; }
       return 0;

@@ -112,6 +112,38 @@ template <int N> SMO_HD void cp_async_wait() {
 #endif
 }
 
+// TMA bulk copy (cp.async.bulk, 1-D) global -> shared with mbarrier completion: ONE thread moves a whole contiguous tile, the
+// bytes travel through the async proxy instead of the LSU / L1 data pipe that the 16-byte cp.async (LDGSTS) copies share with
+// every shared-memory load and store of the FFTs.  Host emulation: an immediate memcpy, waits are no-ops.
+SMO_HD void mbar_init(unsigned long long* bar, int count) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  (void)bar; (void)count;
+#endif
+}
+// called by one thread: arms the barrier with the byte count and starts the copy (bytes: multiple of 16, both sides 16-byte aligned)
+SMO_HD void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+#if defined(__CUDA_ARCH__)
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar), sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa), "l"(gsrc), "r"(bytes), "r"(ba) : "memory");
+#else
+  (void)bar;
+  memcpy(sdst, gsrc, bytes);
+#endif
+}
+SMO_HD void mbar_wait(unsigned long long* bar, unsigned parity) {
+#if defined(__CUDA_ARCH__)
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok = 0;
+  while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(ba), "r"(parity) : "memory");
+#else
+  (void)bar; (void)parity;
+#endif
+}
+
 // Cross-GPU hand-shake fused into a kernel (peer-memory transposes of the slab-decomposed dynamo).  A kernel whose
 // Params carry an `XSync xs` member
 //   * first waits until every source rank has published `wait_epoch` in this GPU's flag words (its inputs were stored

@@ -230,12 +230,18 @@ struct XFParams {
   double scale;
   const cplx* tw;
   int accumulate;            // X_ADJ: outputs 3..5 (x-spectra of (curl G) x B_f) are ADDED to sout[3..5] instead of stored
+  int bulk_u;                // 1: the velocity tile arrives by ONE TMA bulk copy (cp.async.bulk + mbarrier) instead of 16-byte cp.async
+  double* gacc;              // X_ADJ, GACC kernels: running sum of (curl G) x B_f ON THE GRID, tile-major like `ut`
   double* jpart;             // INTEG forward: [gridDim] per-CTA sums of |B|^2 over the grid points this launch visited
 };
 
 // INTEG = Cost_function "Integrated" (KD:655-669, 861-864): the forward pass also sums |B^n|^2 over its grid points
 // (deterministic per-CTA partials), the adjoint pass adds the source -2 B_f to the (curl G) x U products.
-template <class F, int MODE, bool INTEG = false> struct XFused {
+// GACC (adjoint only): the products (curl G) x B_f are not transformed at all inside the sweep: nu = -dt sum_m P_k[F(...)] is
+// linear, so the threads that hold them add them to a running sum on the real grid (tile-major, the layout of `ut`: a warp's
+// read-modify-write of one row group is 512 contiguous bytes, straight from registers) and ONE r2c transform after the sweep
+// replaces 3 of the 6 forward FFTs of every adjoint step; the warps of B_f skip the forward half of the pass.
+template <class F, int MODE, bool INTEG = false, bool GACC = false> struct XFused {
   typedef XFParams Params;
   typedef typename F::Swapped FS;
   static constexpr bool V2 = true;
@@ -267,11 +273,14 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
   // over the time steps is taken on the x-spectra (this kernel adds its (curl G) x B_f outputs to a running array) and
   // the y / z transforms, the transpose and the projection are applied ONCE after the sweep instead of every step.
   // The running array's tile is streamed in with cp.async while the tile is transformed.
-  static constexpr int ACC_ELEMS = (MODE == X_ADJ) ? 3 * NH * T : 0;
-  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS + ACC_ELEMS) * sizeof(cplx);
+  static constexpr int ACC_ELEMS = (MODE == X_ADJ && !GACC) ? 3 * NH * T : 0;
+  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS + ACC_ELEMS + 1) * sizeof(cplx);   // + the mbarrier of the velocity tile
   static_assert(R1 >= R2 && RT == R1, "the radix-R1 stage is the wide one");
   static_assert(SIN_ELEMS % 8 == 0 && SU_UNITS % 8 == 0, "cp.async regions must be whole 128-byte lines");
   static_assert(MODE == X_FWD || MODE == X_ADJ, "fused modes only");
+  static_assert(!GACC || MODE == X_ADJ, "grid accumulation belongs to the adjoint pass");
+  // does field f take part in the forward (r2c) half of the pass?
+  SMO_HD static bool fwd_half(int f) { return !(GACC && f >= 3); }
   static_assert(NH % 2 == 0, "two spectral rows per 128-byte line need an even number of retained modes");
   struct State {
     double re[RT], im[RT];
@@ -295,6 +304,7 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
   SMO_HD static cplx* su_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
   SMO_HD static cplx* x_buf(unsigned char* s) { return su_buf(s) + SU_UNITS; }
   SMO_HD static cplx* acc_buf(unsigned char* s) { return x_buf(s) + X_ELEMS; }
+  SMO_HD static unsigned long long* ubar(unsigned char* s) { return reinterpret_cast<unsigned long long*>(acc_buf(s) + ACC_ELEMS); }
   // unit index of spectral entry (field f, row, tile column col): two rows per 128-byte line
   SMO_HD static int si(int f, int row, int col) {
     return (((f * NH + row) >> 1) << 3) + ((((row & 1) << 2) + col) ^ ((row >> 1) & 3));
@@ -330,7 +340,7 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
   // running-sum tile of the field this warp produces (fields 3..5 only), consumed by phase 8 of the same work item
   SMO_HD static void load_acc(const Params& p, int work, const Ctx& c) {
     const int f = c.tid / FT;
-    if (MODE != X_ADJ || f < 3) return;
+    if (MODE != X_ADJ || GACC || f < 3) return;
     cplx* A = acc_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
     const cplx* src = p.sout[out_field(f)];
@@ -347,14 +357,20 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
       }
     }
   }
+  // the velocity tile is stored in HBM in the (swizzled) order it has in shared memory (UTile below), so it is one contiguous
+  // copy: a single TMA bulk copy issued by one thread (bulk_u), or 16-byte cp.async by everybody
   SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
     cplx* U = su_buf(c.smem);
     const double* src = p.ut + tile_of(p, work) * (3LL * M * 4);
-    for (int q = c.tid; q < SU_UNITS; q += THREADS)            // gmem chunk q = (component, row, half)
-      cp_async16(&U[ui(q / (2 * M), (q / 2) % M, q & 1)], src + 2 * q);
+    if (p.bulk_u) {
+      if (c.tid == 0) bulk_load(U, src, (unsigned)(SU_UNITS * sizeof(cplx)), ubar(c.smem));
+    } else {
+      for (int q = c.tid; q < SU_UNITS; q += THREADS) cp_async16(&U[q], src + 2 * q);
+    }
   }
 
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
+    if (c.tid == 0) mbar_init(ubar(c.smem), 1);
     const cplx w = ldg_c(p.tw + (((c.tid % FT) % LP) < RT ? ((c.tid % FT) % LP) : 0));
     st.wr = w.x; st.wi = w.y;
     st.jacc = 0.0;
@@ -407,8 +423,13 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
     }
     if (PH == 2) {
       if (more) load_sin(p, work + c.ncta, c);   // the spectral buffer was consumed in phase 1
-      if (MODE == X_ADJ && p.accumulate) load_acc(p, work, c);
+      if (MODE == X_ADJ && !GACC && p.accumulate) load_acc(p, work, c);
       cp_async_commit();
+      if (GACC && f >= 3 && wact) {              // the running-sum rows this thread updates in phase 4: on their way into L2
+        const cplx* ga = reinterpret_cast<const cplx*>(p.gacc + tile_of(p, work) * (3LL * M * 4)) + ((f - 2) % 3 * M + jw) * 2 + ppw;
+#pragma unroll
+        for (int i = 0; i < R2; ++i) prefetch_l2(ga + R1 * i * 2);
+      }
       if (wact) {
 #pragma unroll
         for (int j = 0; j < R2; ++j) {
@@ -424,6 +445,7 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
         for (int k2 = 0; k2 < R2; ++k2) Xw[jw + R1 * k2] = make_double2(st.re[k2], st.im[k2]);
       }
       cp_async_wait<1>();                       // the velocity tile of this work item has landed
+      if (p.bulk_u) mbar_wait(ubar(c.smem), (unsigned)(st.it & 1));
     }
     if (PH == 4 && wact) {
       // component (out_field) of the cross product that contains this thread's own field; own values stay in registers
@@ -462,19 +484,32 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
         }
         st.re[i] = e0; st.im[i] = e1;
       }
-      RegFFT<R2, -1>::run(as_arr<R2>(st.re), as_arr<R2>(st.im));
-      twiddle_powers<R2>(st.re, st.im, st.wr, st.wi);
+      if (fwd_half(f)) {
+        RegFFT<R2, -1>::run(as_arr<R2>(st.re), as_arr<R2>(st.im));
+        twiddle_powers<R2>(st.re, st.im, st.wr, st.wi);
+      }
     }
     if (PH == 5) {
       if (more) load_su(p, work + c.ncta, c);    // the velocity buffer was consumed in phase 4
       cp_async_commit();
-      if (wact) {
+      if (wact && fwd_half(f)) {
 #pragma unroll
         for (int k1 = 0; k1 < R2; ++k1) Xw[jw * FS::SK + k1] = make_double2(st.re[k1], st.im[k1]);
       }
+      if (GACC && wact && !fwd_half(f)) {
+        // the (curl G) x B_f products of phase 4 (still in registers) join the running sum on the grid: component c = f-2 (mod 3),
+        // rows jw + R1*i, column pair ppw - 512 contiguous bytes per warp and i.  All loads are issued before the first add, and
+        // nothing waits for this warp until the next tile's product phase: the round trip hides under the other warps' r2c half.
+        cplx* ga = reinterpret_cast<cplx*>(p.gacc + tile_of(p, work) * (3LL * M * 4)) + (((f - 2) % 3) * M + jw) * 2 + ppw;
+        cplx a[R2];
+#pragma unroll
+        for (int i = 0; i < R2; ++i) a[i] = ga[R1 * i * 2];
+#pragma unroll
+        for (int i = 0; i < R2; ++i) ga[R1 * i * 2] = make_double2(a[i].x + st.re[i], a[i].y + st.im[i]);
+      }
     }
     if (PH == 6) {
-      if (nact) {
+      if (nact && fwd_half(f)) {
 #pragma unroll
         for (int j = 0; j < R1; ++j) {
           const cplx v = Xn[j * FS::SK + jn];
@@ -484,22 +519,22 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
       }
     }
     if (PH == 7) {
-      if (nact) {
+      if (nact && fwd_half(f)) {
 #pragma unroll
         for (int k2 = 0; k2 < R1; ++k2) {
           const int k = jn + R2 * k2;   // only the retained modes and their mirror images are needed by phase 8
           if (k < NH || k > M - NH) Xn[k] = make_double2(st.re[k2], st.im[k2]);
         }
       }
-      if (MODE == X_ADJ) cp_async_wait<1>();     // the running-sum tile (committed in phase 2) has landed
+      if (MODE == X_ADJ && !GACC) cp_async_wait<1>();     // the running-sum tile (committed in phase 2) has landed
     }
-    if (PH == 8) {
+    if (PH == 8 && fwd_half(f)) {
       // own thread order (column pairs fastest) so that a row's T columns are stored by adjacent lanes
       const int pp8 = PAIRWARP ? tif / LP : tif % HP, kk = PAIRWARP ? tif % LP : tif / HP;
       const cplx* X8 = x_buf(c.smem) + (f * HP + pp8) * XLP;
       cplx* O = p.sout[out_field(f)] + tile_of(p, work) * T + 2 * pp8;
       const double h = 0.5 * p.scale;
-      const bool addto = (MODE == X_ADJ) && p.accumulate && f >= 3;
+      const bool addto = (MODE == X_ADJ) && !GACC && p.accumulate && f >= 3;
       const cplx* A = acc_buf(c.smem);
       for (int k = kk; k < NH; k += LP) {
         const cplx zk = X8[k];
@@ -513,8 +548,8 @@ template <class F, int MODE, bool INTEG = false> struct XFused {
         O[(long long)k * p.ncols] = o0;
         O[(long long)k * p.ncols + 1] = o1;
       }
-      st.it++;
     }
+    if (PH == 8) st.it++;
   }
 };
 
@@ -525,6 +560,7 @@ struct UTileParams {
   int nwork, nsteps;
   long long ncols;
   int M;
+  int half;      // UnTile: 1 = the half-length layout of xpass_half.cuh ([ncols/4][3][M/2][4][2])
 };
 struct UTile {
   typedef UTileParams Params;
@@ -539,9 +575,34 @@ struct UTile {
     const int n = (int)(work / per_row);
     const long long col = (work % per_row) * THREADS + tid;
     if (col >= p.ncols) return;
+    // unit (16 bytes) = (component, row, column pair), stored at its swizzled shared-memory position XFused::ui()
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc)
-      p.out[(((col / 4) * 3 + cc) * p.M + n) * 4 + (col % 4)] = p.in[cc][(long long)n * p.ncols + col];
+    for (int cc = 0; cc < 3; ++cc) {
+      const long long unit = (((long long)cc * p.M + n) * 2 + (col % 4) / 2) ^ ((n >> 2) & 1);
+      p.out[(col / 4) * (3LL * p.M * 4) + unit * 2 + (col & 1)] = p.in[cc][(long long)n * p.ncols + col];
+    }
+  }
+};
+
+// inverse re-layout (once per adjoint sweep): tile-major running sum [ncols/4][3][M][4] -> grid [3][M][ncols]
+struct UnTile {
+  typedef UTileParams Params;    // in[c] = destination grids (written), out = tile-major source (read)
+  static constexpr int THREADS = 256;
+  static constexpr int NPHASES = 1;
+  static constexpr int MIN_BLOCKS = 1;
+  static constexpr size_t SMEM = 0;
+  struct State {};
+  template <int PH> SMO_HD static void phase(const Params& p, int work, int, int tid, unsigned char*, State&) {
+    const long long per_row = (p.ncols + THREADS - 1) / THREADS;
+    const int n = (int)(work / per_row);
+    const long long col = (work % per_row) * THREADS + tid;
+    if (col >= p.ncols) return;
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const long long src = p.half ? ((((col / 4) * 3 + cc) * (p.M / 2) + n / 2) * 4 + (col % 4)) * 2 + (n & 1)
+                                   : (((col / 4) * 3 + cc) * p.M + n) * 4 + (col % 4);
+      const_cast<double*>(p.in[cc])[(long long)n * p.ncols + col] = p.out[src];
+    }
   }
 };
 

@@ -21,7 +21,7 @@
 
 namespace smo {
 
-template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
+template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> struct XFusedH {
   typedef XFParams Params;
   typedef typename F::Swapped FS;
   static constexpr bool V2 = true;
@@ -44,14 +44,16 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
   static constexpr int SIN_ELEMS = NF * NH * T;      // cplx (16-byte units)
   static constexpr int SU_UNITS = 3 * H * T;         // 16-byte units of the T-column velocity block
   static constexpr int X_ELEMS = NJ * XLP;
-  static constexpr int ACC_ELEMS = (MODE == X_ADJ) ? 3 * NH * T : 0;
-  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS + ACC_ELEMS) * sizeof(cplx);
+  static constexpr int ACC_ELEMS = (MODE == X_ADJ && !GACC) ? 3 * NH * T : 0;   // GACC: running sum on the grid (see XFused)
+  static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS + ACC_ELEMS + 1) * sizeof(cplx);   // + the mbarrier of the velocity tile
   static_assert(R1 >= R2 && RT == R1, "the radix-R1 stage is the wide one");
   static_assert(32 % RT == 0 && FT % WT == 0 && T_ % CPW == 0, "whole FFTs per warp");
   static_assert(T_ == 4, "the shared-memory swizzles assume 4 columns (64 bytes) per row");
-  static_assert(NH % 8 == 0 && H % 8 == 0, "swizzled lines hold two rows; field blocks must start on a swizzle period");
+  static_assert(NH % 8 == 0 && H % 8 == 0 && (CPW == 2 || CPW == 4), "swizzled lines hold whole rows; blocks must start on a swizzle period");
   static_assert(NH <= H && H - NH < NH, "mode bookkeeping of the even/odd assembly");
   static_assert(MODE == X_FWD || MODE == X_ADJ, "fused modes only");
+  static_assert(!GACC || MODE == X_ADJ, "grid accumulation belongs to the adjoint pass");
+  SMO_HD static bool fwd_half(int f) { return !(GACC && f >= 3); }
   struct State {
     double re[RT], im[RT];
     double wr, wi;     // exp(-2 pi i jw / H): base of this thread's inter-stage twiddles of the forward transform (wide mapping)
@@ -73,10 +75,17 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
   SMO_HD static cplx* su_buf(unsigned char* s) { return sin_buf(s) + SIN_ELEMS; }
   SMO_HD static cplx* x_buf(unsigned char* s) { return su_buf(s) + SU_UNITS; }
   SMO_HD static cplx* acc_buf(unsigned char* s) { return x_buf(s) + X_ELEMS; }
-  // two 64-byte rows per 128-byte line, the column index XOR-swizzled by the line number: 8 lanes reading one column of 8
-  // consecutive rows hit 8 different 16-byte bank groups (conflict free), and a cp.async warp fills whole aligned lines
+  SMO_HD static unsigned long long* ubar(unsigned char* s) { return reinterpret_cast<unsigned long long*>(acc_buf(s) + ACC_ELEMS); }
+  // Spectral / running-sum tiles: every warp owns the CPW columns of its FFTs, stored as a block [rows][CPW columns] of its own,
+  // so that the warp's cp.async of 8 consecutive lanes (LROWS rows x CPW columns) fills one ALIGNED 128-byte line in a single
+  // wavefront (r2d ncu: with a row-major [row][4 columns] tile a warp touched half of every line - 11 wavefronts per LDGSTS
+  // instead of 4, a quarter of all shared-memory wavefronts of the kernel).  Inside a line the position is XOR-swizzled by the
+  // line number so that 8 lanes reading one column of 8 consecutive rows hit 8 different 16-byte bank groups.
+  static constexpr int LROWS = 8 / CPW;              // rows per 128-byte line of a warp's block
   SMO_HD static int si(int f, int row, int col) {
-    return (((f * NH + row) >> 1) << 3) + ((((row & 1) << 2) + col) ^ ((row >> 1) & 3));
+    const int g = col / CPW, cc = col % CPW;
+    const int r = (f * (T / CPW) + g) * NH + row;    // row inside the stack of blocks (NH is a multiple of LROWS)
+    return ((r / LROWS) << 3) + (((row % LROWS) * CPW + cc) ^ ((row / LROWS) % CPW));
   }
   SMO_HD static int ui(int cidx, int n, int col) {
     return (((cidx * H + n) >> 1) << 3) + ((((n & 1) << 2) + col) ^ ((n >> 1) & 3));
@@ -101,7 +110,7 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
   }
   SMO_HD static void load_acc(const Params& p, int work, const Ctx& c) {
     const int f = c.tid / FT;
-    if (MODE != X_ADJ || f < 3) return;
+    if (MODE != X_ADJ || GACC || f < 3) return;
     cplx* A = acc_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
     const int tif = c.tid % FT, wv = tif / WT, lane = tif % WT;
@@ -111,14 +120,19 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
       cp_async16(&A[si(f - 3, row, wv * CPW + cc)], src + (long long)row * p.ncols + cc);
     }
   }
+  // the velocity tile is stored in HBM in its (swizzled) shared-memory order (UTileH): one contiguous copy
   SMO_HD static void load_su(const Params& p, int work, const Ctx& c) {
     cplx* U = su_buf(c.smem);
     const double* src = p.ut + tile_of(p, work) * (3LL * M * T);
-    for (int q = c.tid; q < SU_UNITS; q += THREADS)            // gmem unit q = (component, row pair, column)
-      cp_async16(&U[ui(q / (H * T), (q / T) % H, q % T)], src + 2 * q);
+    if (p.bulk_u) {
+      if (c.tid == 0) bulk_load(U, src, (unsigned)(SU_UNITS * sizeof(cplx)), ubar(c.smem));
+    } else {
+      for (int q = c.tid; q < SU_UNITS; q += THREADS) cp_async16(&U[q], src + 2 * q);
+    }
   }
 
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
+    if (c.tid == 0) mbar_init(ubar(c.smem), 1);
     const int jw = (c.tid % FT) % RT;
     const cplx w = ldg_c(p.tw + 2 * jw);            // p.tw[m] = exp(-2 pi i m / M);  exp(-2 pi i jw / H) = tw[2 jw]
     st.wr = w.x; st.wi = w.y;
@@ -173,8 +187,13 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
     }
     if (PH == 2) {
       if (more) load_sin(p, work + c.ncta, c);   // the spectral buffer was consumed in phase 1
-      if (MODE == X_ADJ && p.accumulate) load_acc(p, work, c);
+      if (MODE == X_ADJ && !GACC && p.accumulate) load_acc(p, work, c);
       cp_async_commit();
+      if (GACC && f >= 3) {                      // the running-sum rows this thread updates in phase 4: on their way into L2
+        const cplx* ga = reinterpret_cast<const cplx*>(p.gacc + tile_of(p, work) * (3LL * M * T)) + (((f - 2) % 3) * H + jw) * T + cw;
+#pragma unroll
+        for (int i = 0; i < R2; ++i) prefetch_l2(ga + R1 * i * T);
+      }
 #pragma unroll
       for (int j = 0; j < R2; ++j) {
         const cplx v = Xw[j * F::SK + jw];
@@ -186,6 +205,7 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
 #pragma unroll
       for (int k2 = 0; k2 < R2; ++k2) Xw[jw + R1 * k2] = make_double2(st.re[k2], st.im[k2]);
       cp_async_wait<1>();                       // the velocity tile of this work item has landed
+      if (p.bulk_u) mbar_wait(ubar(c.smem), (unsigned)(st.it & 1));
     }
     if (PH == 4) {
       const cplx* Xa = x_buf(c.smem) + cw * XLP + jw;        // + field * T * XLP + row pair
@@ -220,17 +240,29 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
         }
         st.re[i] = e0; st.im[i] = e1;
       }
-      RegFFT<R2, -1>::run(as_arr<R2>(st.re), as_arr<R2>(st.im));
-      twiddle_powers<R2>(st.re, st.im, st.wr, st.wi);
+      if (fwd_half(f)) {
+        RegFFT<R2, -1>::run(as_arr<R2>(st.re), as_arr<R2>(st.im));
+        twiddle_powers<R2>(st.re, st.im, st.wr, st.wi);
+      }
     }
     if (PH == 5) {
       if (more) load_su(p, work + c.ncta, c);    // the velocity buffer was consumed in phase 4
       cp_async_commit();
+      if (fwd_half(f)) {
 #pragma unroll
-      for (int k1 = 0; k1 < R2; ++k1) Xw[jw * FS::SK + k1] = make_double2(st.re[k1], st.im[k1]);
+        for (int k1 = 0; k1 < R2; ++k1) Xw[jw * FS::SK + k1] = make_double2(st.re[k1], st.im[k1]);
+      } else if (GACC) {
+        // the (curl G) x B_f products of phase 4 (still in registers) join the running sum on the grid (see XFused)
+        cplx* ga = reinterpret_cast<cplx*>(p.gacc + tile_of(p, work) * (3LL * M * T)) + (((f - 2) % 3) * H + jw) * T + cw;
+        cplx a[R2];
+#pragma unroll
+        for (int i = 0; i < R2; ++i) a[i] = ga[R1 * i * T];
+#pragma unroll
+        for (int i = 0; i < R2; ++i) ga[R1 * i * T] = make_double2(a[i].x + st.re[i], a[i].y + st.im[i]);
+      }
     }
     if (PH == 6) {
-      if (nact) {
+      if (nact && fwd_half(f)) {
 #pragma unroll
         for (int j = 0; j < R1; ++j) {
           const cplx v = Xn[j * FS::SK + jn];
@@ -240,19 +272,19 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
       }
     }
     if (PH == 7) {
-      if (nact) {
+      if (nact && fwd_half(f)) {
 #pragma unroll
         for (int k2 = 0; k2 < R1; ++k2) Xn[jn + R2 * k2] = make_double2(st.re[k2], st.im[k2]);   // Z[k], all k (the split needs Z[H-k])
       }
-      if (MODE == X_ADJ) cp_async_wait<1>();     // the running-sum tile (committed in phase 2) has landed
+      if (MODE == X_ADJ && !GACC) cp_async_wait<1>();     // the running-sum tile (committed in phase 2) has landed
     }
-    if (PH == 8) {
+    if (PH == 8 && fwd_half(f)) {
       // own thread order (columns fastest) so that the warp's CPW columns of a row are stored by adjacent lanes
       const int c8 = wv * CPW + lane % CPW, kk = lane / CPW;
       const cplx* X8 = x_buf(c.smem) + (f * T + c8) * XLP;
       cplx* O = p.sout[out_field(f)] + tile_of(p, work) * T + c8;
       const double h = 0.5 * p.scale;
-      const bool addto = (MODE == X_ADJ) && p.accumulate && f >= 3;
+      const bool addto = (MODE == X_ADJ) && !GACC && p.accumulate && f >= 3;
       const cplx* A = acc_buf(c.smem);
       // e^{-2 pi i k/M} for k = kk + RT*t by recurrence
       const cplx w0 = ldg_c(p.tw + kk), ws = ldg_c(p.tw + RT);
@@ -268,8 +300,8 @@ template <class F, int MODE, bool INTEG = false, int T_ = 4> struct XFusedH {
         O[(long long)k * p.ncols] = o;
         const double t = cr * ws.x - ci * ws.y; ci = cr * ws.y + ci * ws.x; cr = t;
       }
-      st.it++;
     }
+    if (PH == 8) st.it++;
   }
 };
 
@@ -286,9 +318,13 @@ struct UTileH {
     const int n = (int)(work / per_row);
     const long long col = (work % per_row) * THREADS + tid;
     if (col >= p.ncols) return;
+    // unit (16 bytes) = (component, row pair, column), stored at its swizzled shared-memory position XFusedH::ui()
+    const int H = p.M / 2, n2 = n / 2, cq = (int)(col % 4);
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc)
-      p.out[((((col / 4) * 3 + cc) * (p.M / 2) + n / 2) * 4 + (col % 4)) * 2 + (n & 1)] = p.in[cc][(long long)n * p.ncols + col];
+    for (int cc = 0; cc < 3; ++cc) {
+      const long long unit = ((((long long)cc * H + n2) >> 1) << 3) + ((((n2 & 1) << 2) + cq) ^ ((n2 >> 1) & 3));
+      p.out[(col / 4) * (3LL * p.M * 4) + unit * 2 + (n & 1)] = p.in[cc][(long long)n * p.ncols + col];
+    }
   }
 };
 

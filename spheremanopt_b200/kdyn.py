@@ -17,6 +17,7 @@ all-to-all transposes inside the library - the replacement of Dedalus' MPI trans
 All arithmetic happens in libsmo_b200.so; there is no CPU fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -68,6 +69,10 @@ class Domain:
             h = C.c_void_p()
             _cabi.check(self.lib, self.lib.smo_kdyn_create(C.byref(h), self.N, self.L, self.rank, self.nranks, self.comm))
         self.h = h
+        # development / A-B switches: SMO_KDYN_OPTS="key=value,..." applies smo_kdyn_set_option to every new Domain
+        for kv in filter(None, os.environ.get("SMO_KDYN_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            _cabi.check(self.lib, self.lib.smo_kdyn_set_option(h, int(k), int(v)))
         self.peer = False
         if self.nranks > 1 and peer_memory:
             # fused transposes: exchange CUDA IPC handles of the pencil buffers so that the FFT passes store straight

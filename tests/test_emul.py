@@ -276,3 +276,61 @@ def test_kdyn_half_length_x_pass_emulated():
         assert abs(-J.value - fo) <= TOL * abs(fo)
         assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
     LH.smo_kdyn_destroy(h)
+
+
+@pytest.mark.parametrize("variant,Npts,nit,every", [("plain", 16, 5, 0), ("plain", 24, 7, 3), ("halfx", 64, 2, 0)])
+def test_kdyn_grid_accumulation_emulated(variant, Npts, nit, every):
+    """SMO_OPT_GRID_ACC: the adjoint x pass sums (curl G) x B_f on the real grid (tile-major) and the r2c transform runs once
+    after the sweep - stored and checkpointed sweeps, both x-pass variants, both costs"""
+    Lv = emul.lib() if variant == "plain" else emul.lib_variant("halfx", ["SMO_TEST_HALFX"])
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    chk = lambda rc: emul._cabi.check(Lv, rc)
+    chk(Lv.smo_kdyn_create(C.byref(h), Npts, od.L, 0, 1, None))
+    chk(Lv.smo_kdyn_set_option(h, emul._cabi.SMO_OPT_GRID_ACC, 1))
+    gsz = Lv.smo_kdyn_grid_elems(h)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    for cost, flag in (("Final", 0), ("Integrated", 2)):
+        J = C.c_double()
+        gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
+        if every:
+            ck = np.zeros(Lv.smo_kdyn_checkpoint_bytes(h, nit, every) // 16, dtype=complex)
+            seg = np.zeros(Lv.smo_kdyn_segment_bytes(h, every) // 16, dtype=complex)
+            chk(Lv.smo_kdyn_forward_ckpt(h, emul.ptr(B0), emul.ptr(U), 2.0, 1e-3, nit, every, emul.ptr(ck), C.byref(J), flag, None))
+            chk(Lv.smo_kdyn_adjoint_ckpt(h, 2.0, 1e-3, nit, every, emul.ptr(ck), emul.ptr(seg), emul.ptr(gB), emul.ptr(gU), flag, None))
+        else:
+            snaps = np.zeros(Lv.smo_kdyn_snapshot_bytes(h, nit) // 16, dtype=complex)
+            chk(Lv.smo_kdyn_forward(h, emul.ptr(B0), emul.ptr(U), 2.0, 1e-3, nit, emul.ptr(snaps), C.byref(J), flag, None))
+            chk(Lv.smo_kdyn_adjoint(h, 2.0, 1e-3, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), flag, None))
+        fo = okd.FWD_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D, cost)
+        go = okd.ADJ_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D, cost)
+        assert abs(-J.value - fo) <= TOL * abs(fo)
+        assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    Lv.smo_kdyn_destroy(h)
+
+
+@pytest.mark.parametrize("variant,Npts,nit", [("plain", 24, 4), ("halfx", 64, 2)])
+def test_kdyn_bulk_velocity_tile_emulated(variant, Npts, nit):
+    """SMO_OPT_BULK_U: the velocity tile lives in HBM in its swizzled shared-memory order and arrives as one contiguous (TMA bulk)
+    copy - checks the pre-swizzled layout of UTile / UTileH against the ui() the x passes read with (together with grid accumulation)"""
+    Lv = emul.lib() if variant == "plain" else emul.lib_variant("halfx", ["SMO_TEST_HALFX"])
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    h = C.c_void_p()
+    chk = lambda rc: emul._cabi.check(Lv, rc)
+    chk(Lv.smo_kdyn_create(C.byref(h), Npts, od.L, 0, 1, None))
+    chk(Lv.smo_kdyn_set_option(h, emul._cabi.SMO_OPT_BULK_U, 1))
+    chk(Lv.smo_kdyn_set_option(h, emul._cabi.SMO_OPT_GRID_ACC, 1))
+    gsz = Lv.smo_kdyn_grid_elems(h)
+    D = okd.GEN_BUFFER(Npts, od, nit)
+    snaps = np.zeros(Lv.smo_kdyn_snapshot_bytes(h, nit) // 16, dtype=complex)
+    J = C.c_double()
+    gB, gU = np.zeros(3 * gsz), np.zeros(3 * gsz)
+    chk(Lv.smo_kdyn_forward(h, emul.ptr(B0), emul.ptr(U), 2.0, 1e-3, nit, emul.ptr(snaps), C.byref(J), 0, None))
+    chk(Lv.smo_kdyn_adjoint(h, 2.0, 1e-3, nit, emul.ptr(snaps), emul.ptr(gB), emul.ptr(gU), 0, None))
+    fo = okd.FWD_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D)
+    go = okd.ADJ_Solve_IVP_Lin([B0, U], od, 2.0, 1e-3, nit, nit, D)
+    assert abs(-J.value - fo) <= TOL * abs(fo)
+    assert relerr(gB, go[0]) <= TOL and relerr(gU, go[1]) <= TOL
+    Lv.smo_kdyn_destroy(h)
