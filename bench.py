@@ -57,14 +57,17 @@ WORKLOADS = {
     "sh23ens": (256, None, 0.1, 500),
     # BASELINE config 1: ONE SH23 problem (the reference's own CPU-runnable case): latency of one f + Grad_f pair
     "sh23": (256, None, 0.1, 500),
+    # BASELINE config 5 as stated: 4096 independent OPTIMISATIONS (unmodified reference optimiser, needs baseline/_ref), 512 per GPU,
+    # every f / Grad_f / Inner_Product call of the ensemble served by batched launches (spheremanopt_b200/ensemble.py)
+    "sh23opt": (256, None, 0.1, 500),
     # rows A5/B5, C1-C3: vector kernels on dynamo-sized vectors (3 * 192^3 doubles = 170 MB each, > L2)
     "vec": (128, None, None, None),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
 # named in NCU_SOURCE (it also reads the forward state from its snapshot slot and read-modify-writes the running sum of the
-# gradient integrand; algorithmic model 566.2 MB)
-NCU_TRAFFIC = {("kdyn128", 1): 695.0e6}
-NCU_SOURCE = {("kdyn128", 1): "ncu --set full, build r1g (profiles/r1g_kdyn128_adj_step_ncu.txt)"}
+# gradient integrand on the real grid - 340 MB that replace three r2c transforms; algorithmic model 566.2 MB)
+NCU_TRAFFIC = {("kdyn128", 1): 803.7e6}
+NCU_SOURCE = {("kdyn128", 1): "ncu --set full, build r2f (profiles/r2f_kdyn128_xadj_ncu.txt): 566.3 MB read + 237.4 MB written"}
 METRIC = "Grad_f evals/s (fwd+adjoint)"
 UNIT = "Grad_f evals/s"
 # fp64 work of one SH23 instance pair (~138 GFLOP per 4096-instance pair at N_ITERS = 500): per time step one
@@ -637,6 +640,94 @@ def sh23_full_optimisation(sh23):
             "J_final": float(FUN[-1]), "residual_final": float(RES[0][-1])}
 
 
+def run_gpu_sh23opt(args):
+    """config 5 as stated: 4096 / world independent optimisations per GPU (M_0 swept over [0.05, 0.1]), the UNMODIFIED reference
+    optimiser in one thread per instance, all calls of one kind served by ONE batched launch (ensemble.SH23Ensemble).
+    One step = the whole ensemble optimised from its initial fields (max_iters = $SMO_ENS_ITERS, default 20)."""
+    import contextlib
+    import tempfile
+    import warnings
+    torch, dist, world, rank, local = _init_dist()
+    from spheremanopt_b200 import _cabi, sh23
+    from spheremanopt_b200.ensemble import SH23Ensemble
+    lib = _cabi.load()
+    ref = None
+    for d in (os.environ.get("SMO_REFERENCE_DIR"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if d and os.path.isfile(os.path.join(d, "Sphere_Grad_Descent.py")):
+            ref = d
+            break
+    if ref is None:
+        if rank == 0:
+            print(json.dumps({"metric": "SH23 optimisations/s", "unavailable": "reference optimiser not staged (tools/stage_reference.py)"}))
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests", "refstubs")); sys.path.insert(0, ref)
+    import Sphere_Grad_Descent as SGD
+    N, _, dt, nit = WORKLOADS[args.workload]
+    total = int(os.environ.get("SMO_ENS_TOTAL", "4096"))
+    iters = int(os.environ.get("SMO_ENS_ITERS", "20"))
+    nb = total // world
+    dom, X0 = sh23.Generate_IC(0.0725, N, device="cuda:%d" % local)
+    M0 = np.linspace(0.05, 0.1, total)[rank * nb:(rank + 1) * nb]
+    X0s = [np.sqrt(m / 0.0725) * X0 for m in M0]
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    times, last = [], None
+    n0 = lib.smo_launch_count()
+    try:
+        for s_ in range(args.warmup + args.steps):
+            ens = SH23Ensemble(nb, dom, dt, nit)
+
+            def one(i, f, g, ip):
+                try:
+                    return SGD.Optimise_On_Multi_Sphere([X0s[i]], [float(M0[i])], f, g, ip, [dom, dt, nit, nit, None, None, "Discrete"], (dom, None),
+                                                        max_iters=iters, alpha_k=np.pi, LS='LS_wolfe', CG=True, callback=None, verbose=False)
+                except TypeError:
+                    # the reference's own failure mode, kept as is (SURVEY appendix B): a failed Wolfe search leaves g_k = None and the
+                    # next iteration raises (SGD:740-741, 758); the instance has terminated
+                    return None
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(sys.stderr), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                out = ens.run(one)
+            torch.cuda.synchronize()
+            dt_s = time.perf_counter() - t0
+            if s_ >= args.warmup:
+                times.append(dt_s)
+            last = (ens, out)
+    finally:
+        os.chdir(cwd)
+    launches = lib.smo_launch_count() - n0
+    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dom.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ens, out = last
+        crashed = sum(1 for o in out if o is None)
+        out = [o for o in out if o is not None]
+        its = [len(o[1]) for o in out] or [0]
+        sec = float(t.item())
+        line = {"metric": "SH23 optimisations/s (unmodified Optimise_On_Multi_Sphere, batched CUDA callables)", "value": total / sec, "unit": "optimisations/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak" if False else "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 5: %d independent SH23 optimisations (Npts=256, dt=0.1, N_ITERS=500, M_0 in [0.05,0.1], LS_wolfe + CG, alpha_k=pi, "
+                                       "max_iters=%d), %d per GPU, one optimiser thread per instance, calls served by batched launches; one step = the whole ensemble"
+                                       % (total, iters, nb), "instances": total, "max_iters": iters},
+                "ensemble": {"iterations_min_mean_max": [int(min(its)), float(np.mean(its)), int(max(its))],
+                             "ended_by_the_reference_line_search_failure": crashed,
+                             "batched_rounds": ens.rounds, "calls_served": ens.served,
+                             "mean_group_size": {k: (ens.served[k] / max(ens.rounds[k], 1)) for k in ens.rounds},
+                             "J_final_first_last": ([float(out[0][1][-1]), float(out[-1][1][-1])] if out else None)},
+                "gpu_launches": int(launches),
+                "e2e": {"value": total / sec, "unit": "optimisations/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                        "note": "host vectors in and out of every call (Mode H); the figure above IS end to end"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_gpu_vec(args):
     """rows A5/B5, C1-C3: Inner_Product, axpby, tangent/transport projection, retraction on dynamo-sized device vectors"""
     torch, dist, world, rank, local = _init_dist()
@@ -720,6 +811,8 @@ def main():
         run_reference(args)
     elif args.workload in ("sh23ens", "sh23"):
         run_gpu_sh23ens(args)
+    elif args.workload == "sh23opt":
+        run_gpu_sh23opt(args)
     elif args.workload == "vec":
         run_gpu_vec(args)
     else:

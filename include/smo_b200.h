@@ -40,10 +40,15 @@ long long smo_launch_count(void);
 /* Replaces FWD_Solve_Build_Lin (SH:279-332): Npts Fourier modes on [0,L), parameter a (= -0.3 at SH:309). */
 int smo_sh23_create(smo_sh23_t** h, int Npts, double L, double a);
 int smo_sh23_destroy(smo_sh23_t* h);
-/* bytes of snapshot storage per instance for n_iters steps: (n_iters+1)*(Npts/2) complex128 (GEN_BUFFER, SH:238-272) */
+/* bytes of snapshot storage per instance for n_iters steps (GEN_BUFFER, SH:238-272).  The store is opaque: every forward state
+ * is kept ON THE GRID ((n_iters+1)*M doubles: what the adjoint's pointwise product consumes, written straight from the
+ * registers of the forward solve's c2r transform) plus the coefficients of the final state (Npts/2 complex);
+ * smo_sh23_snapshot_coef converts a stored state back to the reference's coefficient form A_fwd[:, n]. */
 size_t smo_sh23_snapshot_bytes(const smo_sh23_t* h, int n_iters);
+/* coefficients [batch][Npts/2] complex128 of stored state n (0..n_iters) of every instance (inspection / tests / side outputs) */
+int smo_sh23_snapshot_coef(smo_sh23_t* h, const void* snaps_dev, int batch, int n_iters, int n, void* coef_dev, void* stream);
 /* Replaces FWD_Solve_IVP_Lin (SH:409-545) for `batch` independent instances.
- * X_dev [batch][M] in; snaps_dev [batch][n_iters+1][Npts/2] complex128 out; J_dev [batch] out with
+ * X_dev [batch][M] in; snaps_dev [batch][smo_sh23_snapshot_bytes] out; J_dev [batch] out with
  * J = dt*sum_{n=0..n_iters} mean(u_n^2)  (the reference returns -J, SH:545). */
 int smo_sh23_forward(smo_sh23_t* h, const double* X_dev, int batch, double dt, int n_iters, void* snaps_dev,
                      double* J_dev, void* stream);
@@ -151,7 +156,8 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
  * CTA one after the other, so that the remote stores of the first items drain over NVLink while the later ones compute. */
 #define SMO_OPT_PUSH_WAVES 5
 /* SMO_OPT_TWO_STREAMS: 1 = the z chunks of the y -> fused x -> y section (smo_kdyn_set_chunks) alternate between two CUDA
- * streams, so that one chunk's NVLink transfer and hand-shake overlap the other chunk's x pass; 0 (default) = one stream. */
+ * streams; 2 = the same as a software pipeline (a kernel of chunk c+1 starts after the same kernel of chunk c), so that one
+ * chunk's NVLink transfer and hand-shake run beside the next chunk's x pass; 0 (default) = one stream. */
 #define SMO_OPT_TWO_STREAMS 6
 /* SMO_OPT_GRID_ACC: 1 (default) = the fused adjoint x pass adds its (curl G) x B_f products to a running sum ON THE GRID (tile-major,
  * read-modify-write straight from registers) and skips their r2c transform; one transform after the sweep replaces 3 of the 6
@@ -186,6 +192,8 @@ int smo_vec_dot(const double* x_dev, const double* y_dev, long long n, double sc
                 void* work_dev, void* stream);
 /* the same without the D2H copy / synchronisation: the scaled sum is left in ((double*)work_dev)[0] */
 int smo_vec_dot_dev(const double* x_dev, const double* y_dev, long long n, double scale, void* work_dev, void* stream);
+/* batched form for many short vectors (ensembles): out_dev[r] = scale * sum_j x[r][j]*y[r][j], r < rows; one launch, no sync */
+int smo_vec_dot_rows(const double* x_dev, const double* y_dev, int rows, long long len, double scale, double* out_dev, void* stream);
 /* 64-bit position-sensitive checksum of the bit patterns of x (sum_i bits(x_i)*(2i+1) mod 2^64): the host layer's identity check
  * of the X a snapshot store was filled for (the f -> Grad_f coupling of SGD:740-796).  Synchronises the stream. */
 int smo_vec_checksum(const double* x_dev, long long n, unsigned long long* out_host, void* work_dev, void* stream);

@@ -24,6 +24,7 @@ SIGNATURES = {
     "smo_sh23_create": (i32, [C.POINTER(vp), i32, f64, f64]),
     "smo_sh23_destroy": (i32, [vp]),
     "smo_sh23_snapshot_bytes": (sz, [vp, i32]),
+    "smo_sh23_snapshot_coef": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "smo_sh23_forward": (i32, [vp, dp, i32, f64, i32, vp, dp, vp]),
     "smo_sh23_adjoint": (i32, [vp, i32, f64, i32, vp, dp, i32, vp]),
     "smo_sh23_prep": (i32, [vp, dp, i32, f64, i32, dp, vp]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "smo_vec_dot": (i32, [dp, dp, ll, f64, C.POINTER(f64), vp, vp]),
     "smo_vec_dot_dev": (i32, [dp, dp, ll, f64, vp, vp]),
     "smo_microbench_dfma": (i32, [dp, i32, i32, C.POINTER(f64), vp]),
+    "smo_vec_dot_rows": (i32, [dp, dp, i32, ll, f64, dp, vp]),
     "smo_vec_checksum": (i32, [dp, ll, C.POINTER(C.c_ulonglong), vp, vp]),
     "smo_vec_axpby": (i32, [f64, dp, f64, dp, dp, ll, vp]),
     "smo_vec_project": (i32, [dp, dp, dp, ll, vp, vp]),

@@ -192,6 +192,33 @@ struct FinalSum {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// Row-wise inner products of two [rows][len] matrices: out[r] = a * sum_j x[r][j]*y[r][j].  One CTA per row, fixed summation
+// order.  The batched Inner_Product of the ensemble driver (many small SH23 vectors per launch instead of one launch each).
+struct VecRowDot {
+  typedef VecParams Params;       // n = row length, nwork = rows, out[rows]
+  static constexpr int THREADS = VTHREADS;
+  static constexpr int NPHASES = 2;
+  static constexpr int MIN_BLOCKS = 1;
+  static constexpr size_t SMEM = VTHREADS * sizeof(double);
+  struct State {};
+  template <int PH>
+  SMO_HD static void phase(const Params& p, int work, int, int tid, unsigned char* smem, State&) {
+    double* S = reinterpret_cast<double*>(smem);
+    if (PH == 0) {
+      const double* x = p.x + (long long)work * p.n;
+      const double* y = p.y + (long long)work * p.n;
+      double a = 0.0;
+      for (long long j = tid; j < p.n; j += VTHREADS) a += x[j] * y[j];
+      S[tid] = a;
+    } else if (tid == 0) {
+      double s = 0.0;
+      for (int t = 0; t < VTHREADS; ++t) s += S[t];
+      p.out[work] = p.a * s;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // 64-bit position-sensitive checksum of a vector's bit patterns: sum_i bits(x_i) * (2 i + 1) mod 2^64.  Used by the host
 // layer to notice that the snapshot store Grad_f is about to replay was written for a different X (the reference couples
 // f and Grad_f through that store); one streaming pass, deterministic, any single changed entry changes it.

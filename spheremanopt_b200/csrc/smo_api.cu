@@ -257,6 +257,13 @@ extern "C" int smo_vec_dot_dev(const double* x, const double* y, long long n, do
   TRY((vec_launch<V_DOT>(x, y, nullptr, n, 0, 0, 0, w, st)));
   return final_sum(w, n, 1, scale, st);
 }
+extern "C" int smo_vec_dot_rows(const double* x, const double* y, int rows, long long len, double scale, double* out, void* stream) {
+  if (!x || !y || !out || rows <= 0 || len <= 0) return fail(SMO_E_ARG, "smo_vec_dot_rows: bad argument");
+  VecParams p;
+  memset(&p, 0, sizeof p);
+  p.x = x; p.y = y; p.out = out; p.n = len; p.a = scale; p.nwork = rows; p.nsteps = 1;
+  return launch<VecRowDot>(p, (rt_stream)stream);
+}
 extern "C" int smo_vec_checksum(const double* x, long long n, unsigned long long* out_host, void* work, void* stream) {
   if (!x || !out_host || !work || n <= 0) return fail(SMO_E_ARG, "smo_vec_checksum: bad argument");
   rt_stream st = (rt_stream)stream;
@@ -351,6 +358,8 @@ template <int H> static int sh23_run(smo_sh23* h, bool adj, Sh23Params& p, rt_st
 }
 static int sh23_dispatch(smo_sh23* h, bool adj, Sh23Params& p, rt_stream st) {
   p.nwork = (p.batch + SH_NI - 1) / SH_NI;
+  if (p.xstride == 0) p.xstride = h->M;
+  if (p.n_iters >= 0) p.sstride = (long long)(smo_sh23_snapshot_bytes(h, p.n_iters) / sizeof(double));
   p.Nh = h->Nh; p.a = h->a; p.kfac = 2.0 * 3.14159265358979323846 / h->L; p.inv_dt = 1.0 / p.dt;
   p.twH = h->twH; p.twM = h->twM;
   switch (h->H) {
@@ -381,8 +390,9 @@ extern "C" int smo_sh23_destroy(smo_sh23_t* h) {
   delete h;
   return 0;
 }
+// per instance: (n_iters+1) states on the grid (M doubles each) + the coefficients of the final state (Nh complex)
 extern "C" size_t smo_sh23_snapshot_bytes(const smo_sh23_t* h, int n_iters) {
-  return h ? sizeof(cplx) * (size_t)(n_iters + 1) * h->Nh : 0;
+  return h ? sizeof(double) * (size_t)(n_iters + 1) * h->M + sizeof(cplx) * (size_t)h->Nh : 0;
 }
 static int sh23_args(smo_sh23* h, int batch, double dt, int n_iters, const char* who) {
   if (!h) return fail(SMO_E_ARG, "%s: null handle", who);
@@ -395,7 +405,7 @@ extern "C" int smo_sh23_forward(smo_sh23_t* h, const double* X, int batch, doubl
   if (!X || !snaps || !J) return fail(SMO_E_ARG, "smo_sh23_forward: null buffer");
   Sh23Params p;
   memset(&p, 0, sizeof p);
-  p.X = X; p.snaps = (cplx*)snaps; p.J = J; p.batch = batch; p.n_iters = n_iters; p.dt = dt; p.flags = 0;
+  p.X = X; p.snaps = (double*)snaps; p.J = J; p.batch = batch; p.n_iters = n_iters; p.dt = dt; p.flags = 0;
   p.nsteps = n_iters + 3;
   return sh23_dispatch(h, false, p, (rt_stream)stream);
 }
@@ -410,12 +420,24 @@ extern "C" int smo_sh23_prep(smo_sh23_t* h, const double* X, int batch, double d
   return sh23_dispatch(h, false, p, (rt_stream)stream);
 }
 static int sh23_reserve(smo_sh23* h, int batch, int n_iters);
+static int sh23_coef_of(smo_sh23* h, const double* X, long long xstride, int batch, void* coef, rt_stream st) {
+  Sh23Params p;
+  memset(&p, 0, sizeof p);
+  p.X = X; p.xstride = xstride; p.cout = (cplx*)coef; p.batch = batch; p.n_iters = 0; p.dt = 1.0; p.flags = 8;
+  p.nsteps = 1;    // step 0 only: r2c of the input, coefficients -> cout
+  return sh23_dispatch(h, false, p, st);
+}
 extern "C" int smo_sh23_to_coef(smo_sh23_t* h, const double* X, int batch, void* coef, void* stream) {
   TRY(sh23_args(h, batch, 1.0, 0, "smo_sh23_to_coef"));
   if (!X || !coef) return fail(SMO_E_ARG, "smo_sh23_to_coef: null buffer");
-  TRY(sh23_reserve(h, batch, -1));
-  // a forward solve of zero steps stores snapshot 0 = trunc(FFT(X))/M
-  return smo_sh23_forward(h, X, batch, 1.0, 0, coef, h->jout, stream);
+  return sh23_coef_of(h, X, h->M, batch, coef, (rt_stream)stream);
+}
+// coefficients [batch][Nh] of stored state n of every instance of a filled snapshot store (inspection: the reference's A_fwd[:, n])
+extern "C" int smo_sh23_snapshot_coef(smo_sh23_t* h, const void* snaps, int batch, int n_iters, int n, void* coef, void* stream) {
+  TRY(sh23_args(h, batch, 1.0, n_iters, "smo_sh23_snapshot_coef"));
+  if (!snaps || !coef || n < 0 || n > n_iters) return fail(SMO_E_ARG, "smo_sh23_snapshot_coef: bad argument");
+  const long long sstride = (long long)(smo_sh23_snapshot_bytes(h, n_iters) / sizeof(double));
+  return sh23_coef_of(h, (const double*)snaps + (long long)n * h->M, sstride, batch, coef, (rt_stream)stream);
 }
 extern "C" int smo_sh23_to_grid(smo_sh23_t* h, const void* coef, int batch, double* out, void* stream) {
   TRY(sh23_args(h, batch, 1.0, 0, "smo_sh23_to_grid"));
@@ -432,7 +454,7 @@ extern "C" int smo_sh23_adjoint(smo_sh23_t* h, int batch, double dt, int n_iters
   if (!snaps || !grad) return fail(SMO_E_ARG, "smo_sh23_adjoint: null buffer");
   Sh23Params p;
   memset(&p, 0, sizeof p);
-  p.snaps = (cplx*)snaps; p.grad = grad; p.batch = batch; p.n_iters = n_iters; p.dt = dt;
+  p.snaps = (double*)const_cast<void*>(snaps); p.grad = grad; p.batch = batch; p.n_iters = n_iters; p.dt = dt;
   p.flags = (flags & SMO_ADJOINT_CONTINUOUS) ? 1 : 0;
   p.nsteps = n_iters + 2;
   return sh23_dispatch(h, true, p, (rt_stream)stream);
@@ -540,7 +562,7 @@ struct smo_kdyn {
                                 // chunk overlap the x pass of the next)
   unsigned int* err_host; unsigned int* err_dev;   // host-mapped error word of the bounded hand-shake waits
 #if !defined(SMO_EMUL)
-  cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
+  cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join, ev_pipe[3];
 #endif
 };
 // flag words of one rank: [which][chunk][source rank]; which = 0 barrier kernel, XS_A, XS_B
@@ -974,14 +996,19 @@ template <int M> struct KdOps {
     // two streams: odd chunks run on an auxiliary stream, so that the remote stores (and the hand-shake) of one chunk's last
     // y pass drain while the other chunk is still in its x pass.  Works eagerly and inside a stream capture (fork / join events).
     const bool two = h->two_streams && nch > 1;
+    // two_streams = 2: software pipeline - a kernel of chunk c+1 starts only after the SAME kernel of chunk c (events), so the
+    // chunks are staggered by one stage: chunk c's pushing y pass (NVLink transfer + hand-shake) runs beside chunk c+1's x pass
+    // instead of both chunks marching in lock step (r2c: unstaggered chunks gained nothing).
+    const bool stagger = two && h->two_streams >= 2;
     if (two && !h->aux_stream) {
       CUDA_TRY(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
       CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_pipe[k], cudaEventDisableTiming));
     }
     if (two) { CUDA_TRY(cudaEventRecord(h->ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0)); }
 #else
-    const bool two = false;
+    const bool two = false, stagger = false;
 #endif
     for (int ch = 0; ch < nch; ++ch) {
       const int z0 = ch * nzc, zc = nch > 1 ? nzc : -1;
@@ -990,10 +1017,29 @@ template <int M> struct KdOps {
 #else
       rt_stream q = st;
 #endif
-      TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, q, z0, zc, (ch == 0 || two) ? XS_B : XS_NONE, true));
+#if !defined(SMO_EMUL)
+#define SMO_STAGE_GATE(k)                                                                              \
+      if (stagger) {                                                                                   \
+        if (ch > 0) CUDA_TRY(cudaStreamWaitEvent(q, h->ev_pipe[k], 0));                                 \
+      }
+#define SMO_STAGE_DONE(k)                                                                              \
+      if (stagger && ch + 1 < nch) CUDA_TRY(cudaEventRecord(h->ev_pipe[k], q));
+#else
+#define SMO_STAGE_GATE(k)
+#define SMO_STAGE_DONE(k)
+#endif
+      SMO_STAGE_GATE(0)
+      TRY(inv_y(h, h->p1t, mode == 0 ? xs : h->p2, 3, q, z0, zc, (ch == 0 || (two && !stagger)) ? XS_B : XS_NONE, true));
+      SMO_STAGE_DONE(0)
+      SMO_STAGE_GATE(1)
       if (mode == 0) TRY(x_fwd(h, xs, q, z0, zc, integ));
       else TRY(x_adj(h, xs, q, z0, zc, integ));
+      SMO_STAGE_DONE(1)
+      SMO_STAGE_GATE(2)
       TRY(fwd_y(h, h->p2, h->p1t, 3, q, z0, zc, kernel_sync(h) ? XS_A : XS_NONE, true, ch, eA));
+      SMO_STAGE_DONE(2)
+#undef SMO_STAGE_GATE
+#undef SMO_STAGE_DONE
     }
 #if !defined(SMO_EMUL)
     if (two) { CUDA_TRY(cudaEventRecord(h->ev_join, h->aux_stream)); CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0)); }
@@ -1117,7 +1163,7 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
 }
 static int graph_opts(const smo_kdyn* h) {
   return ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
-         (h->two_streams ? 16 : 0) | ((h->push_waves & 3) << 5) | (h->grid_acc ? 128 : 0) | (h->bulk_u ? (1 << 28) : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
+         ((h->two_streams & 1) ? 16 : 0) | ((h->two_streams & 2) ? (1 << 29) : 0) | ((h->push_waves & 3) << 5) | (h->grid_acc ? 128 : 0) | (h->bulk_u ? (1 << 28) : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
 }
 
 // ---- snapshot store ------------------------------------------------------------------------------------------------
@@ -1468,7 +1514,7 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
   }
   rt_free(h->flags); rt_free(h->counters); rt_free(h->epoch_dev);
   if (h->err_host) cudaFreeHost(h->err_host);
-  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); for (int k = 0; k < 3; ++k) cudaEventDestroy(h->ev_pipe[k]); }
   if (h->graphs) {
     for (GraphEntry& e : h->graphs->e) if (e.exec) cudaGraphExecDestroy(e.exec);
     cudaStreamDestroy(h->graphs->stream); cudaEventDestroy(h->graphs->ev0); cudaEventDestroy(h->graphs->ev1);
@@ -1635,7 +1681,7 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
     case SMO_OPT_PEER_PULL: h->peer_pull = value ? 1 : 0; return 0;
     case SMO_OPT_L2_HINTS: h->l2_hints = value ? 1 : 0; return 0;
     case SMO_OPT_PUSH_WAVES: h->push_waves = value < 1 ? 1 : value; return 0;
-    case SMO_OPT_TWO_STREAMS: h->two_streams = value ? 1 : 0; return 0;
+    case SMO_OPT_TWO_STREAMS: h->two_streams = value < 0 ? 0 : (value > 2 ? 2 : value); return 0;
     case SMO_OPT_GRID_ACC: h->grid_acc = value ? 1 : 0; return 0;
     case SMO_OPT_BULK_U: h->bulk_u = value ? 1 : 0; return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic

@@ -22,19 +22,23 @@ import torch
 
 
 class Rendezvous:
-    """K workers, three batched services.  ``batched[kind](ids, args_list) -> list of results`` (ids ascending)."""
+    """K workers, three batched services.  ``batched[kind](ids, args_list) -> list of results`` (ids ascending).
+
+    Scales to hundreds of instances per GPU (config 5: 512 per GPU): every worker parks on an event of its OWN, and whoever
+    completes a group wakes exactly the workers it served (no notify_all herd); worker threads get small stacks."""
 
     def __init__(self, n, batched_f, batched_grad, batched_ip):
         self.n = int(n)
         self.batched = {"f": batched_f, "grad": batched_grad, "ip": batched_ip}
-        self.cv = threading.Condition()
+        self.lock = threading.Lock()
+        self.wake = {}           # id -> threading.Event of the parked worker
         self.pending = {}        # id -> (kind, args)
         self.results = {}        # id -> result or exception
         self.live = 0
         self.rounds = {"f": 0, "grad": 0, "ip": 0}     # batched backend calls made (for reporting)
         self.served = {"f": 0, "grad": 0, "ip": 0}     # individual calls served
 
-    # -- called with self.cv held: serve one kind if every live worker is parked
+    # -- called with self.lock held: serve one kind after the other while every live worker is parked
     def _serve_if_ready(self):
         while self.pending and len(self.pending) == self.live:
             # the kind most workers wait for goes first (keeps groups large)
@@ -55,14 +59,16 @@ class Rendezvous:
             for i, r in zip(ids, out):
                 del self.pending[i]
                 self.results[i] = r
-            self.cv.notify_all()
+                self.wake[i].set()
 
     def call(self, i, kind, args):
-        with self.cv:
+        ev = self.wake[i]
+        with self.lock:
+            ev.clear()
             self.pending[i] = (kind, args)
             self._serve_if_ready()
-            while i not in self.results:
-                self.cv.wait()
+        ev.wait()
+        with self.lock:
             r = self.results.pop(i)
         if isinstance(r, Exception):
             raise r
@@ -84,15 +90,27 @@ class Rendezvous:
             except Exception as e:
                 out[i] = e
             finally:
-                with self.cv:
+                with self.lock:
                     self.live -= 1
                     self._serve_if_ready()      # the others may all be parked already
 
-        with self.cv:
+        with self.lock:
             self.live = len(ids)
-        threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in ids]
-        for t in threads:
-            t.start()
+            self.wake = {i: threading.Event() for i in ids}
+        old = threading.stack_size()
+        try:
+            threading.stack_size(1 << 20)       # hundreds of workers: 1 MB stacks instead of the platform default (8 MB)
+        except (ValueError, RuntimeError):
+            pass
+        try:
+            threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in ids]
+            for t in threads:
+                t.start()
+        finally:
+            try:
+                threading.stack_size(old)
+            except (ValueError, RuntimeError):
+                pass
         for t in threads:
             t.join()
         for i in ids:
@@ -104,7 +122,7 @@ class Rendezvous:
 class SH23Ensemble(Rendezvous):
     """Batched CUDA backends for K independent SH23 problems on one GPU (host vectors in, host vectors out).
 
-    Every instance owns one row of a persistent snapshot store [K][N_ITERS+1][Npts/2]; a group of instances is solved in a
+    Every instance owns one row of a persistent snapshot store [K][smo_sh23_snapshot_bytes]; a group of instances is solved in a
     compact temporary store and its rows are scattered to / gathered from the persistent one, so ``Grad_f`` of an instance
     always replays the forward solve of the same instance whatever the grouping was."""
 
@@ -112,8 +130,8 @@ class SH23Ensemble(Rendezvous):
         from . import sh23
         self._sh = sh23
         self.domain, self.dt, self.nit, self.adj = domain, float(dt), int(N_ITERS), Adjoint_type
-        self.row = (self.nit + 1) * domain.Nh
-        self.store = torch.zeros(n, self.row, dtype=torch.complex128, device=domain.device)
+        self.row = domain.lib.smo_sh23_snapshot_bytes(domain.h, self.nit) // 8     # doubles per instance (opaque store)
+        self.store = torch.zeros(n, self.row, dtype=torch.float64, device=domain.device)
         self.tag = [None] * n
         self._tmp = {}
         super().__init__(n, self._f, self._grad, self._ip)
@@ -152,7 +170,14 @@ class SH23Ensemble(Rendezvous):
         return [[G[k].copy()] for k in range(len(ids))]
 
     def _ip(self, ids, pairs):
-        x = self._stack([p[0] for p in pairs]).view(len(ids), -1)
-        y = self._stack([p[1] for p in pairs]).view(len(ids), -1)
-        ops = self.domain.vecops(x.shape[1])
-        return [ops.dot(x[k], y[k], 1.0 / self.domain.M) for k in range(len(ids))]
+        # ONE launch for the whole group (smo_vec_dot_rows: one CTA per instance), one D2H of len(ids) doubles
+        from . import _cabi
+        from .devvec import _stream_ptr
+        x = self._stack([p[0] for p in pairs])
+        y = self._stack([p[1] for p in pairs])
+        n = x.numel() // len(ids)
+        out = torch.empty(len(ids), dtype=torch.float64, device=self.domain.device)
+        with torch.cuda.device(self.domain.device):
+            _cabi.check(self.domain.lib, self.domain.lib.smo_vec_dot_rows(x.data_ptr(), y.data_ptr(), len(ids), n, 1.0 / self.domain.M,
+                                                                         out.data_ptr(), _stream_ptr()))
+        return out.cpu().tolist()

@@ -66,24 +66,33 @@ class Domain:
 class SnapshotStore(dict):
     """Device-resident replacement of the reference's ``{'A_fwd': complex128[Npts/2, N_SUB_ITERS+1]}`` (SH:266-272).
 
-    Layout in HBM: [batch][N_SUB_ITERS+1][Npts/2] complex128 (a snapshot is one contiguous 2 KB row).  ``['A_fwd']``
-    returns a host copy in the reference's [Npts/2, N_SUB_ITERS+1] orientation for inspection."""
+    Opaque HBM store: per instance the N_SUB_ITERS+1 forward states ON THE GRID (M doubles each: what the adjoint's pointwise
+    product reads; written from the registers of the forward solve) + the coefficients of the final state.  ``['A_fwd']``
+    converts back (one r2c launch per state) and returns a host copy in the reference's [Npts/2, N_SUB_ITERS+1] orientation."""
 
     def __init__(self, domain, n_iters, batch=1):
         super().__init__()
         self.domain, self.n_iters, self.batch = domain, int(n_iters), int(batch)
-        nbytes = domain.lib.smo_sh23_snapshot_bytes(domain.h, self.n_iters) * self.batch
-        self.buf = torch.zeros(nbytes // 16, dtype=torch.complex128, device=domain.device)
+        self.inst_bytes = domain.lib.smo_sh23_snapshot_bytes(domain.h, self.n_iters)
+        self.buf = torch.zeros(self.inst_bytes * self.batch // 8, dtype=torch.float64, device=domain.device)
         self.valid = False
 
     def ptr(self):
         return self.buf.data_ptr()
 
+    def coef(self, n):
+        """coefficients [batch][Npts/2] of stored state n (device tensor)"""
+        c = torch.empty(self.batch * self.domain.Nh, dtype=torch.complex128, device=self.domain.device)
+        with torch.cuda.device(self.domain.device):
+            _cabi.check(self.domain.lib, self.domain.lib.smo_sh23_snapshot_coef(self.domain.h, self.ptr(), self.batch, self.n_iters, int(n),
+                                                                                c.data_ptr(), _stream_ptr()))
+        return c.view(self.batch, self.domain.Nh)
+
     def __getitem__(self, key):
         if key != 'A_fwd':
             raise KeyError(key)
-        a = self.buf.view(self.batch, self.n_iters + 1, self.domain.Nh).cpu().numpy()
-        return a[0].T.copy() if self.batch == 1 else np.transpose(a, (0, 2, 1)).copy()
+        a = torch.stack([self.coef(n) for n in range(self.n_iters + 1)], dim=2).cpu().numpy()     # [batch][Nh][n]
+        return a[0].copy() if self.batch == 1 else a.copy()
 
 
 def GEN_BUFFER(domain, N_SUB_ITERS, Npts=256, batch=1):

@@ -27,18 +27,23 @@ def test_sh23_emulated(L, Npts):
     X = np.stack([sh23_input(od, seed=b, amp=0.04 + 0.003 * b) for b in range(batch)])
     h = C.c_void_p()
     emul.check(L.smo_sh23_create(C.byref(h), Npts, od.L, -0.3))
-    snaps = np.zeros((batch, nit + 1, od.Nh), dtype=complex)
+    nb = L.smo_sh23_snapshot_bytes(h, nit) // 8      # opaque store: [nit+1][M] grid values + Nh final coefficients per instance
+    snaps = np.zeros((batch, nb))
     J = np.zeros(batch); G = np.zeros((batch, od.M)); Gc = np.zeros((batch, od.M))
     emul.check(L.smo_sh23_forward(h, emul.ptr(X), batch, dt, nit, emul.ptr(snaps), emul.ptr(J), None))
     emul.check(L.smo_sh23_adjoint(h, batch, dt, nit, emul.ptr(snaps), emul.ptr(G), 0, None))
     emul.check(L.smo_sh23_adjoint(h, batch, dt, nit, emul.ptr(snaps), emul.ptr(Gc), 1, None))
     P = np.zeros((batch, od.M))
     emul.check(L.smo_sh23_prep(h, emul.ptr(X), batch, 0.01, 5, emul.ptr(P), None))
+    A = np.zeros((nit + 1, batch, od.Nh), dtype=complex)
+    for n in range(nit + 1):
+        emul.check(L.smo_sh23_snapshot_coef(h, emul.ptr(snaps), batch, nit, n, emul.ptr(A[n]), None))
     for b in range(batch):
         D = osh.GEN_BUFFER(od, nit)
         fo = osh.FWD_Solve_IVP_Lin([X[b]], od, dt, nit, nit, D)
         assert abs(-J[b] - fo) <= TOL * abs(fo)
-        assert relerr(snaps[b].T, D['A_fwd']) <= TOL
+        assert relerr(A[:, b, :].T, D['A_fwd']) <= TOL
+        assert relerr(snaps[b, 3 * od.M:4 * od.M], od.to_grid_1d(D['A_fwd'][:, 3])) <= TOL      # the store holds grid values
         assert relerr(G[b], osh.ADJ_Solve_IVP_Lin([X[b]], od, dt, nit, nit, D)[0]) <= TOL
         assert relerr(Gc[b], osh.ADJ_Solve_IVP_Lin([X[b]], od, dt, nit, nit, D, None, "Continuous")[0]) <= TOL
         assert relerr(P[b], osh.FWD_Solve_IVP_PREP(X[b], od, 0.01, 5)) <= TOL

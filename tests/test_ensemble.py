@@ -129,3 +129,43 @@ def test_sh23_ensemble_on_gpu():
         Xo, ho = _descent(X0[i], M0[i], lambda X: osh.FWD_Solve_IVP_Lin(X, od, dt, nit, nit, D),
                           lambda X: osh.ADJ_Solve_IVP_Lin(X, od, dt, nit, nit, D), lambda a, b: osh.Inner_Prod(a, b, od), iters[i])
         assert np.allclose(out[i][1], ho, rtol=1e-9, atol=0)
+
+
+def test_rendezvous_scales_to_many_workers():
+    """256 workers with drifting call sequences: per-worker wake-ups, no lost wake-up, every call served exactly once"""
+    from spheremanopt_b200.ensemble import Rendezvous
+    K = 256
+    calls = {"f": 0, "grad": 0, "ip": 0}
+
+    def bf(ids, args):
+        calls["f"] += 1
+        return [float(i) + a for i, a in zip(ids, args)]
+
+    def bg(ids, args):
+        calls["grad"] += 1
+        return [[2.0 * a] for a in args]
+
+    def bi(ids, args):
+        calls["ip"] += 1
+        return [x * y for x, y in args]
+    R = Rendezvous(K, bf, bg, bi)
+
+    def target(i, f, g, ip):
+        acc = 0.0
+        for it in range(3 + i % 5):              # different lengths: workers finish at different times
+            acc += f(1.0 * it)
+            if (i + it) % 3 == 0:
+                acc += g(0.5)[0]
+            for _ in range(i % 4):
+                acc += ip(2.0, 0.25)
+        return acc
+    out = R.run(target)
+    for i in range(K):
+        want = 0.0
+        for it in range(3 + i % 5):
+            want += i + it
+            if (i + it) % 3 == 0:
+                want += 1.0
+            want += 0.5 * (i % 4)
+        assert out[i] == want
+    assert R.served["f"] == sum(3 + i % 5 for i in range(K)) and calls["f"] == R.rounds["f"] < R.served["f"] / 20
