@@ -146,13 +146,15 @@ template <class F> struct Sh23Core {
 };
 
 // ------------------------------------------------------------------------------------------------ forward
-template <class F, int NI_> struct Sh23Fwd {
+// MB_ = resident CTAs per SM the register allocation is bounded for (8: ensembles; 2: few instances, latency bound - the compiler
+// may keep more of a step in flight)
+template <class F, int NI_, int MB_ = SMO_SH_MB> struct Sh23Fwd {
   typedef Sh23Params Params;
   typedef Sh23Core<F> Cr;
   static constexpr int NI = NI_, RT = F::RT, R1 = F::R1, R2 = F::R2, M = Cr::M;
   static constexpr int THREADS = NI_ * RT;
   static constexpr int NPHASES = 6;
-  static constexpr int MIN_BLOCKS = SMO_SH_MB;
+  static constexpr int MIN_BLOCKS = MB_;
   static constexpr size_t SMEM = Cr::template smem_bytes<NI_>();
   // an instance is private to its RT threads: with RT dividing 32 every barrier of the time loop is a __syncwarp; the shared
   // 1/A_k table is written in step 0 and first read in step 1, with the CTA barrier after phase 5 of step 0 in between
@@ -262,13 +264,13 @@ template <class F, int NI_> struct Sh23Fwd {
 };
 
 // ------------------------------------------------------------------------------------------------ adjoint
-template <class F, int NI_> struct Sh23Adj {
+template <class F, int NI_, int MB_ = SMO_SH_MB> struct Sh23Adj {
   typedef Sh23Params Params;
   typedef Sh23Core<F> Cr;
   static constexpr int NI = NI_, RT = F::RT, R1 = F::R1, R2 = F::R2, M = Cr::M;
   static constexpr int THREADS = NI_ * RT;
   static constexpr int NPHASES = 6;
-  static constexpr int MIN_BLOCKS = SMO_SH_MB;
+  static constexpr int MIN_BLOCKS = MB_;
   static constexpr size_t SMEM = Cr::template smem_bytes<NI_>();
   SMO_HD static constexpr int sync_after(int ph) { return (32 % RT == 0 && ph != 5) ? 1 : 2; }
   struct State {

@@ -353,8 +353,11 @@ constexpr int SH_NI = 4;
 
 template <int H> static int sh23_run(smo_sh23* h, bool adj, Sh23Params& p, rt_stream st) {
   typedef typename FacOf<H>::type F;
-  if (adj) return launch<Sh23Adj<F, SH_NI>>(p, st);
-  return launch<Sh23Fwd<F, SH_NI>>(p, st);
+  // few instances (a single optimisation: BASELINE config 1): latency bound, occupancy is irrelevant - the variant compiled
+  // without the 128-register bound; ensembles: 8 CTAs per SM
+  const bool few = p.nwork <= 2 * 148;
+  if (adj) return few ? launch<Sh23Adj<F, SH_NI, 2>>(p, st) : launch<Sh23Adj<F, SH_NI>>(p, st);
+  return few ? launch<Sh23Fwd<F, SH_NI, 2>>(p, st) : launch<Sh23Fwd<F, SH_NI>>(p, st);
 }
 static int sh23_dispatch(smo_sh23* h, bool adj, Sh23Params& p, rt_stream st) {
   p.nwork = (p.batch + SH_NI - 1) / SH_NI;

@@ -183,9 +183,11 @@ SMO_HD unsigned long long xs_load_flag(const unsigned long long* f) {
   return *(const volatile unsigned long long*)f;
 #endif
 }
+// (the release ordering comes from ONE system-wide fence before the first flag store: a st.release per peer compiles to one
+//  MEMBAR.ALL.SYS per store - 8 serial fences in the last CTA at 8 GPUs, seen in the r2 SASS)
 SMO_HD void xs_store_flag(unsigned long long* f, unsigned long long v) {
 #if defined(__CUDA_ARCH__) && !defined(SMO_XSYNC_RELAXED)
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
 #else
   *(volatile unsigned long long*)f = v;
 #endif
@@ -313,6 +315,8 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const ty
           *p.xs.counter = 0u;   // ready for the next launch
 #if defined(SMO_XSYNC_RELAXED)
           __threadfence();
+#else
+          __threadfence_system();   // acquire side of the CTA count + release of the whole launch's stores, once for all flag stores
 #endif
           const unsigned long long val = p.xs.sig_epoch + (p.xs.sig_base ? *p.xs.sig_base : 0ull);
           for (int s = 0; s < p.xs.sig_n; ++s) xs_store_flag(p.xs.sig_flags[s] + p.xs.sig_rank, val);
