@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmo_b200.so")
+# (SMO_B200_LIB: development only - an alternative build of the same sources, e.g. a tuning variant under build/)
+LIB_PATH = os.environ.get("SMO_B200_LIB") or os.path.join(_HERE, "libsmo_b200.so")
 
 vp, dp, ll, i32, f64, sz = C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_double, C.c_size_t
 
@@ -86,6 +87,7 @@ SMO_OPT_PUSH_WAVES = 5
 SMO_OPT_TWO_STREAMS = 6
 SMO_OPT_GRID_ACC = 7
 SMO_OPT_BULK_U = 8
+SMO_OPT_TMA_SIN = 9
 
 
 def bind(cdll):

@@ -559,6 +559,9 @@ struct smo_kdyn {
   int l2_hints;                 // 1: L2 residency hints on the pencil data of the time loops (single rank)
   int peer_pull;                // 0 (default, measured faster on 2 B200): producers push; 1: consumers pull from the peers' buffers
   int bulk_u;                   // 1: the x passes fetch their velocity tile with one TMA bulk copy per tile
+  int tma_sin;                  // 1: ... and their spectral tiles with TMA tensor copies (tensor maps cached per source array)
+  struct TmCache* tmc;          // registered x-spectral arrays (work block, snapshot store, checkpoint segment) and their tensor maps
+  cplx* p2block;                // the six y-padded work arrays are one allocation (one tensor map, slice = field)
   int grid_acc; double* accg;   // 1: the adjoint x pass sums (curl G) x B_f on the real grid (tile-major, 3*gsize doubles) instead of on the x-spectra
   int push_waves;               // pushing kernels run ~push_waves work items per CTA so that remote stores drain under compute
   int two_streams;              // 1: the z chunks of the y -> x -> y section alternate between two streams (transfers of one
@@ -741,6 +744,69 @@ static void xs_wait(smo_kdyn* h, XSync& xs, int which, int nch = 1) {
   xs.err = h->err_dev;
 }
 
+// ---- TMA tensor maps of the x-spectral arrays ------------------------------------------------------------------------
+// An x-spectral array is [slices][Nh][ncols] complex (slices = fields x stored states, contiguous).  The fused x passes fetch a
+// 4-column (or 2-column) x Nh-row box of one slice per tensor copy; the map (cuTensorMapEncodeTiled: FLOAT64 elements,
+// dims {2*ncols, Nh, slices}, hardware swizzle matching the kernels' si()) depends only on the array, so it is cached.
+struct TmEntry { const cplx* base; long long nslices; int box_cols, box_rows; SmoTensorMap map; bool have; };
+struct TmCache { std::vector<TmEntry> e; };
+static void tm_destroy(smo_kdyn* h) { delete h->tmc; h->tmc = nullptr; }
+// (re)register an array the x passes may read spectral tiles from
+static void tm_register(smo_kdyn* h, const void* base, long long nslices) {
+  if (!h->tmc) h->tmc = new TmCache();
+  for (TmEntry& t : h->tmc->e)
+    if (t.base == (const cplx*)base) { if (t.nslices != nslices) { t.nslices = nslices; t.have = false; } return; }
+  if (h->tmc->e.size() >= 16) h->tmc->e.erase(h->tmc->e.begin() + 1);     // (entry 0 = the handle's own work block)
+  TmEntry t; t.base = (const cplx*)base; t.nslices = nslices; t.box_cols = t.box_rows = 0; t.have = false;
+  h->tmc->e.push_back(t);
+}
+#if !defined(SMO_EMUL)
+typedef CUresult (*tm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tm_encode_fn tm_encoder() {
+  static tm_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (tm_encode_fn)q;
+    else (void)cudaGetLastError();
+  }
+  return fn;
+}
+#endif
+// tensor map + slice index of the x-spectral field at `ptr`; false: not inside a registered array / no TMA -> the launch uses cp.async
+static bool tm_resolve(smo_kdyn* h, const cplx* ptr, int box_cols, int box_rows, SmoTensorMap* out, int* z) {
+#if defined(SMO_EMUL)
+  (void)h; (void)ptr; (void)box_cols; (void)box_rows; (void)out; (void)z;
+  return false;
+#else
+  if (!h->tmc) return false;
+  for (TmEntry& t : h->tmc->e) {
+    if (ptr < t.base || ptr >= t.base + (size_t)t.nslices * h->p2size) continue;
+    if ((size_t)(ptr - t.base) % h->p2size) return false;
+    if (!t.have || t.box_cols != box_cols || t.box_rows != box_rows) {
+      tm_encode_fn enc = tm_encoder();
+      if (!enc) return false;
+      const cuuint64_t ncols = (cuuint64_t)h->M * h->nz;
+      const cuuint64_t dims[3] = {2 * ncols, (cuuint64_t)h->Nh, (cuuint64_t)t.nslices};
+      const cuuint64_t strides[2] = {ncols * sizeof(cplx), (cuuint64_t)h->p2size * sizeof(cplx)};
+      const cuuint32_t box[3] = {(cuuint32_t)(2 * box_cols), (cuuint32_t)box_rows, 1};
+      const cuuint32_t es[3] = {1, 1, 1};
+      const CUtensorMapSwizzle sw = (box_cols * sizeof(cplx) == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+      if (enc(&t.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)t.base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+      t.have = true; t.box_cols = box_cols; t.box_rows = box_rows;
+    }
+    *out = t.map;
+    *z = (int)((size_t)(ptr - t.base) / h->p2size);
+    return true;
+  }
+  return false;
+#endif
+}
+
 // ---- pass launchers ---------------------------------------------------------------------------------------
 // which fused x pass serves grid length M: the pair-packed XFused (two real columns per complex FFT of length M), or - where M
 // has no 16-thread factorisation (M = 384) - the half-length XFusedH (one real column per complex FFT of length M/2)
@@ -887,10 +953,26 @@ template <int M> struct KdOps {
     XFParams p; xffill(p, h, 4, 0, nch > 1 ? h->nz / nch : -1);
     return (size_t)nch * (size_t)grid_for<XK<X_FWD, true>>(p.nwork);
   }
+  // TMA path of the spectral tiles: tensor map + slice of every input field (fields 0..2 share one array, fields 3..5 another)
+  template <class K> static void tma_sources(smo_kdyn* h, XFParams& p, int nf) {
+    p.tma_sin = 0;
+    if (!h->tma_sin || !K::TMA_OK) return;
+    for (int g = 0; g < nf / 3; ++g) {
+      for (int c = 0; c < 3; ++c) {
+        SmoTensorMap m; int z = 0;
+        if (!tm_resolve(h, p.sin[3 * g + c], K::TMA_BOX_COLS, K::TMA_BOX_ROWS, &m, &z)) return;
+        if (c == 0) p.tm[g] = m;
+        else if (memcmp(&m, &p.tm[g], sizeof m) != 0) return;      // the three components must live in one array
+        p.tz[3 * g + c] = z;
+      }
+    }
+    p.tma_sin = 1;
+  }
   // forward: x-spectra of B (the snapshot slot or the work arrays) in, x-spectra of U x B out (work arrays)
   static int x_fwd(smo_kdyn* h, cplx* const* bp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
     XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = bp2[f]; p.sout[f] = h->p2[f]; }
+    tma_sources<XK<X_FWD, false>>(h, p, 3);
     int rc;
     if (integ) {   // cost "Integrated": this launch's per-CTA sums of |B|^2 go to the next free slots of jparts
       const int grid = grid_for<XK<X_FWD, true>>(p.nwork);
@@ -909,6 +991,7 @@ template <int M> struct KdOps {
   static int x_adj(smo_kdyn* h, cplx* const* bfp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
     XFParams p; xffill(p, h, 4, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = h->p2[f]; p.sout[f] = h->p2[f]; p.sin[3 + f] = bfp2[f]; }
+    tma_sources<XK<X_ADJ, false, true>>(h, p, 6);
     p.accumulate = 1;
     prof_begin(h, PK_XA, st);
     int rc;
@@ -1166,7 +1249,7 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
 }
 static int graph_opts(const smo_kdyn* h) {
   return ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
-         ((h->two_streams & 1) ? 16 : 0) | ((h->two_streams & 2) ? (1 << 29) : 0) | ((h->push_waves & 3) << 5) | (h->grid_acc ? 128 : 0) | (h->bulk_u ? (1 << 28) : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
+         ((h->two_streams & 1) ? 16 : 0) | ((h->two_streams & 2) ? (1 << 29) : 0) | ((h->push_waves & 3) << 5) | (h->grid_acc ? 128 : 0) | (h->bulk_u ? (1 << 28) : 0) | (h->tma_sin ? (1 << 30) : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
 }
 
 // ---- snapshot store ------------------------------------------------------------------------------------------------
@@ -1265,6 +1348,7 @@ static int jparts_finish(smo_kdyn* h, size_t used, double dt, double scale, doub
 template <int M> static int kd_forward(smo_kdyn* h, const double* B0, const double* U, double Rm, double dt, int n_iters,
                                        void* snaps, double* J_host, int flags, rt_stream st) {
   const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
+  tm_register(h, snaps, (long long)(n_iters + 1) * 3);
   TRY(kd_set_U<M>(h, U, st));
   if (integ) TRY(jparts_begin<M>(h, n_iters, st));
   TRY(KdOps<M>::to_coef(h, B0, h->G, st));
@@ -1331,6 +1415,7 @@ template <int M> static int kd_adjoint(smo_kdyn* h, double Rm, double dt, int n_
   const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
   const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   void* snaps = const_cast<void*>(snapsc);
+  tm_register(h, snaps, (long long)(n_iters + 1) * 3);
   cplx* s[3];
   snap_final(h, snaps, n_iters, s);
   TRY(KdOps<M>::compat(h, s, Rm, dt, cont | (integ ? 1 : 0), st));
@@ -1380,6 +1465,7 @@ template <int M> static int kd_adjoint_ckpt(smo_kdyn* h, double Rm, double dt, i
   const int cont = (flags & SMO_ADJOINT_CONTINUOUS) ? 2 : 0;
   const bool integ = (flags & SMO_COST_INTEGRATED) != 0;
   void* ck = const_cast<void*>(ckc);
+  tm_register(h, seg, (long long)(every + 1) * 3);
   cplx* s[3];
   snap_ptrs(h, ck, ckpt_slot_of(n_iters, n_iters, every), s);
   TRY(KdOps<M>::compat(h, s, Rm, dt, cont | (integ ? 1 : 0), st));
@@ -1458,6 +1544,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->graphs = nullptr; h->capturing = 0; h->cap_a0 = h->cap_b0 = 0; h->epoch_dev = nullptr;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
   h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0; h->l2_hints = 1;
+  h->tma_sin = 0; h->tmc = nullptr; h->p2block = nullptr;
   h->grid_acc = 1; h->accg = nullptr; h->bulk_u = 1;     // (r2e: adjoint x pass 221 -> 196 us at 128^3, 2.46 -> 2.04 ms at 256^3)
   h->push_waves = 1; h->two_streams = 0; h->err_host = nullptr; h->err_dev = nullptr;
 #if !defined(SMO_EMUL)
@@ -1482,7 +1569,8 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
       if (nranks > 1) rc = rt_malloc((void**)&h->p1t[f], sizeof(cplx) * h->p1size);
       else h->p1t[f] = h->p1[f];
     }
-    if (rc == 0) rc = rt_malloc((void**)&h->p2[f], sizeof(cplx) * h->p2size);
+    if (rc == 0 && f == 0) rc = rt_malloc((void**)&h->p2block, sizeof(cplx) * h->p2size * MAXF);
+    if (rc == 0) h->p2[f] = h->p2block + (size_t)f * h->p2size;
     if (rc == 0) rc = rt_malloc((void**)&h->cw[f], sizeof(cplx) * h->csize);
   }
   for (int c = 0; c < 3 && rc == 0; ++c) {
@@ -1491,6 +1579,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
     if (rc == 0) rc = rt_malloc((void**)&h->W[c], sizeof(cplx) * h->csize);
     if (rc == 0) rc = rt_malloc((void**)&h->Ug[c], sizeof(double) * h->gsize);
   }
+  if (rc == 0) tm_register(h, h->p2block, MAXF);
   if (rc == 0) rc = rt_malloc((void**)&h->Ut, sizeof(double) * 3 * h->gsize);
   if (rc == 0) rc = rt_malloc((void**)&h->gwork, sizeof(double) * 3 * h->gsize);
   if (rc == 0) rc = rt_malloc((void**)&h->vwork, smo_vec_work_bytes((long long)(3 * h->gsize)));
@@ -1503,10 +1592,11 @@ extern "C" int smo_kdyn_destroy(smo_kdyn_t* h) {
   rt_free(h->tw);
   for (int f = 0; f < MAXF; ++f) {
     if (h->nranks > 1) rt_free(h->p1t[f]);
-    rt_free(h->p1[f]); rt_free(h->p2[f]); rt_free(h->cw[f]);
+    rt_free(h->p1[f]); rt_free(h->cw[f]);
   }
   for (int c = 0; c < 3; ++c) { rt_free(h->G[c]); rt_free(h->NU[c]); rt_free(h->W[c]); rt_free(h->Ug[c]); rt_free(h->acc[c]); }
-  rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut); rt_free(h->jparts); rt_free(h->accg);
+  rt_free(h->gwork); rt_free(h->vwork); rt_free(h->Ut); rt_free(h->jparts); rt_free(h->accg); rt_free(h->p2block);
+  tm_destroy(h);
 #if !defined(SMO_EMUL)
   if (h->peer_on) {
     for (int s = 0; s < h->nranks; ++s) {
@@ -1687,6 +1777,7 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
     case SMO_OPT_TWO_STREAMS: h->two_streams = value < 0 ? 0 : (value > 2 ? 2 : value); return 0;
     case SMO_OPT_GRID_ACC: h->grid_acc = value ? 1 : 0; return 0;
     case SMO_OPT_BULK_U: h->bulk_u = value ? 1 : 0; return 0;
+    case SMO_OPT_TMA_SIN: h->tma_sin = value ? 1 : 0; return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic
       for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) { h->peer_p1[f][s2] = h->p1[f]; h->peer_p1t[f][s2] = h->p1t[f]; }
       return 0;

@@ -22,10 +22,13 @@
 #include <vector>
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+struct alignas(64) SmoTensorMap { unsigned long long opaque[16]; };
 #else
 #include <cuda_runtime.h>
+#include <cuda.h>
 #define SMO_HD __host__ __device__ __forceinline__
 #define SMO_DEV __device__ __forceinline__
+typedef CUtensorMap SmoTensorMap;     // TMA descriptor (cuTensorMapEncodeTiled), passed to kernels by value inside their Params
 #endif
 
 namespace smo {
@@ -132,6 +135,25 @@ SMO_HD void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned lon
 #else
   (void)bar;
   memcpy(sdst, gsrc, bytes);
+#endif
+}
+// arrive on the barrier and add `bytes` to the transaction count it waits for (one call per issuing thread)
+SMO_HD void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+#else
+  (void)bar; (void)bytes;
+#endif
+}
+// TMA tensor copy (cp.async.bulk.tensor, 3-D tiled map) global -> shared: one thread moves a whole box {c0.., c1.., c2} described
+// by the tensor map (row pitch, swizzle and bounds live in the descriptor); completion is signalled on the mbarrier.
+SMO_HD void tma_load_3d(void* sdst, const SmoTensorMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(reinterpret_cast<unsigned long long>(tm)),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+#else
+  (void)sdst; (void)tm; (void)c0; (void)c1; (void)c2; (void)bar;
 #endif
 }
 SMO_HD void mbar_wait(unsigned long long* bar, unsigned parity) {
@@ -272,8 +294,8 @@ template <class K, int PH> struct PhaseStep<K, PH, true> {
 
 // One CTA loops over work items blockIdx.x, blockIdx.x + gridDim.x, ... (persistent-style grid).
 template <class K>
-__global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const typename K::Params p) {
-  extern __shared__ __align__(128) unsigned char smo_smem[];
+__global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const __grid_constant__ typename K::Params p) {
+  extern __shared__ __align__(1024) unsigned char smo_smem[];     // (TMA swizzle patterns are functions of the shared-memory address)
   typename K::State st;
   if constexpr (has_xsync<K>::value) {
     if (p.xs.wait_flags != nullptr) {

@@ -231,6 +231,10 @@ struct XFParams {
   const cplx* tw;
   int accumulate;            // X_ADJ: outputs 3..5 (x-spectra of (curl G) x B_f) are ADDED to sout[3..5] instead of stored
   int bulk_u;                // 1: the velocity tile arrives by ONE TMA bulk copy (cp.async.bulk + mbarrier) instead of 16-byte cp.async
+  int tma_sin;               // 1: the spectral tiles arrive by TMA tensor copies (one per field, box = 4 columns x NH rows, hardware
+                             // swizzle = si()) described by tm[0] (fields 0..2) / tm[1] (fields 3..5), slice tz[f] of the map
+  int tz[MAXF];
+  SmoTensorMap tm[2];
   double* gacc;              // X_ADJ, GACC kernels: running sum of (curl G) x B_f ON THE GRID, tile-major like `ut`
   double* jpart;             // INTEG forward: [gridDim] per-CTA sums of |B|^2 over the grid points this launch visited
 };
@@ -305,6 +309,9 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false> struct XFuse
   SMO_HD static cplx* x_buf(unsigned char* s) { return su_buf(s) + SU_UNITS; }
   SMO_HD static cplx* acc_buf(unsigned char* s) { return x_buf(s) + X_ELEMS; }
   SMO_HD static unsigned long long* ubar(unsigned char* s) { return reinterpret_cast<unsigned long long*>(acc_buf(s) + ACC_ELEMS); }
+  SMO_HD static unsigned long long* sbar(unsigned char* s) { return ubar(s) + 1; }     // mbarrier of the spectral tiles (TMA path)
+  static constexpr bool TMA_OK = !PAIRWARP && (NH * T * (int)sizeof(cplx)) % 1024 == 0;   // every field's tile starts on a swizzle period
+  static constexpr int TMA_BOX_COLS = T, TMA_BOX_ROWS = NH;                              // box of one tensor copy
   // unit index of spectral entry (field f, row, tile column col): two rows per 128-byte line
   SMO_HD static int si(int f, int row, int col) {
     return (((f * NH + row) >> 1) << 3) + ((((row & 1) << 2) + col) ^ ((row >> 1) & 3));
@@ -324,6 +331,15 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false> struct XFuse
     cplx* S = sin_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
     const int f = c.tid / FT;
+    if (TMA_OK && p.tma_sin) {
+      // one TMA tensor copy per field, issued by the first lane of the field's warp (the warp has just finished reading its tile:
+      // no other warp touches it); SWIZZLE_64B of the descriptor == si()
+      if (c.tid % FT == 0) {
+        mbar_expect_tx(sbar(c.smem), (unsigned)(NH * T * sizeof(cplx)));
+        tma_load_3d(&S[f * NH * T], &p.tm[f >= 3 ? 1 : 0], (int)(col0 * 2), 0, p.tz[f], sbar(c.smem));
+      }
+      return;
+    }
     if constexpr (PAIRWARP) {   // the warp of pair pp streams in the two columns it assembles
       const int pp = (c.tid % FT) / LP;
       for (int q = c.tid % LP; q < NH * 2; q += LP) {
@@ -370,7 +386,7 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false> struct XFuse
   }
 
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
-    if (c.tid == 0) mbar_init(ubar(c.smem), 1);
+    if (c.tid == 0) { mbar_init(ubar(c.smem), 1); mbar_init(sbar(c.smem), NF); }
     const cplx w = ldg_c(p.tw + (((c.tid % FT) % LP) < RT ? ((c.tid % FT) % LP) : 0));
     st.wr = w.x; st.wi = w.y;
     st.jacc = 0.0;
@@ -396,6 +412,7 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false> struct XFuse
         load_su(p, work, c); cp_async_commit();
       }
       cp_async_wait<1>();                       // the spectral tile of this work item has landed
+      if (TMA_OK && p.tma_sin) mbar_wait(sbar(c.smem), (unsigned)(st.it & 1));
     }
     if (PH == 1) {
       if (nact) {

@@ -76,6 +76,9 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> 
   SMO_HD static cplx* x_buf(unsigned char* s) { return su_buf(s) + SU_UNITS; }
   SMO_HD static cplx* acc_buf(unsigned char* s) { return x_buf(s) + X_ELEMS; }
   SMO_HD static unsigned long long* ubar(unsigned char* s) { return reinterpret_cast<unsigned long long*>(acc_buf(s) + ACC_ELEMS); }
+  SMO_HD static unsigned long long* sbar(unsigned char* s) { return ubar(s) + 1; }     // mbarrier of the spectral tiles (TMA path)
+  static constexpr bool TMA_OK = (NH * CPW * (int)sizeof(cplx)) % 1024 == 0;           // every warp's block starts on a swizzle period
+  static constexpr int TMA_BOX_COLS = CPW, TMA_BOX_ROWS = NH;                          // box of one tensor copy
   // Spectral / running-sum tiles: every warp owns the CPW columns of its FFTs, stored as a block [rows][CPW columns] of its own,
   // so that the warp's cp.async of 8 consecutive lanes (LROWS rows x CPW columns) fills one ALIGNED 128-byte line in a single
   // wavefront (r2d ncu: with a row-major [row][4 columns] tile a warp touched half of every line - 11 wavefronts per LDGSTS
@@ -102,6 +105,14 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> 
     cplx* S = sin_buf(c.smem);
     const long long col0 = tile_of(p, work) * T;
     const int f = c.tid / FT, tif = c.tid % FT, wv = tif / WT, lane = tif % WT;
+    if (TMA_OK && p.tma_sin) {
+      // one TMA tensor copy per warp: box = its CPW columns x NH rows; SWIZZLE_32B (CPW = 2) / SWIZZLE_64B (CPW = 4) == si()
+      if (lane == 0) {
+        mbar_expect_tx(sbar(c.smem), (unsigned)(NH * CPW * sizeof(cplx)));
+        tma_load_3d(&S[(f * (T / CPW) + wv) * NH * CPW], &p.tm[f >= 3 ? 1 : 0], (int)((col0 + wv * CPW) * 2), 0, p.tz[f], sbar(c.smem));
+      }
+      return;
+    }
     const cplx* src = p.sin[f] + col0 + wv * CPW;
     for (int q = lane; q < NH * CPW; q += WT) {
       const int cc = q % CPW, row = q / CPW;
@@ -132,7 +143,7 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> 
   }
 
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
-    if (c.tid == 0) mbar_init(ubar(c.smem), 1);
+    if (c.tid == 0) { mbar_init(ubar(c.smem), 1); mbar_init(sbar(c.smem), NF * (T / CPW)); }
     const int jw = (c.tid % FT) % RT;
     const cplx w = ldg_c(p.tw + 2 * jw);            // p.tw[m] = exp(-2 pi i m / M);  exp(-2 pi i jw / H) = tw[2 jw]
     st.wr = w.x; st.wi = w.y;
@@ -158,6 +169,7 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> 
         load_su(p, work, c); cp_async_commit();
       }
       cp_async_wait<1>();                       // the spectral tile of this work item has landed
+      if (TMA_OK && p.tma_sin) mbar_wait(sbar(c.smem), (unsigned)(st.it & 1));
     }
     if (PH == 1) {
       if (nact) {
