@@ -14,8 +14,9 @@ driver's contract; see DESIGN.md section "Measurement" for the definition of eve
  * e2e    - the same pair through the reference-facing callables with HOST (pinned numpy) vectors in and numpy
             gradients out, H2D/D2H copies inside the timed region, over the same number of steps; the copy times
             (h2d_ms / d2h_ms per step, CUDA events around copies of the same buffers) are printed next to it;
- * roofline - the dominant kernel (fused adjoint x-pass), CUDA-event timed per launch inside the timed region,
-            algorithmic bytes per SURVEY.md section 8(d);
+ * roofline - the dominant kernel (fused adjoint x-pass), CUDA-event timed per launch (event-record nodes inside the replayed
+            graphs) over a SECOND pass of the same K steps right after the headline region - the event nodes cost a few us
+            per launch, which round 1 had charged to `value`; algorithmic bytes per SURVEY.md section 8(d);
  * cpu_baseline - the numpy/scipy oracle (a port, not Dedalus) on the box's host cores, bounded sample;
  * mp_parity_relerr (N > 1) - worst relative error of J / Grad_f of a 32^3, 6-step run on the SAME process group against
             the oracle, taken before the timed region: multi-GPU parity evidence inside the scaling record.

@@ -166,7 +166,7 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
 /* SMO_OPT_BULK_U: 1 (default) = the fused x passes fetch the velocity tile of a column tile (18 KB at 128^3, stored in HBM in its
  * swizzled shared-memory order) with ONE TMA bulk copy (cp.async.bulk + mbarrier) instead of 16-byte cp.async copies. */
 #define SMO_OPT_BULK_U 8
-/* SMO_OPT_TMA_SIN: 1 = the fused x passes fetch their spectral tiles (4 columns x Npts/2 rows per field, 64-byte pieces at the
+/* SMO_OPT_TMA_SIN: 1 (default) = the fused x passes fetch their spectral tiles (4 columns x Npts/2 rows per field, 64-byte pieces at the
  * row pitch of the x-spectral arrays) with TMA tensor copies (cp.async.bulk.tensor, 3-D tiled maps with hardware swizzle,
  * one copy per field and tile) instead of 16-byte cp.async copies; 0 = cp.async. */
 #define SMO_OPT_TMA_SIN 9

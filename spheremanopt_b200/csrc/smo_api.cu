@@ -1544,7 +1544,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->graphs = nullptr; h->capturing = 0; h->cap_a0 = h->cap_b0 = 0; h->epoch_dev = nullptr;
   h->peer_on = 0; h->flags = nullptr; h->epoch = 0;
   h->inkernel_sync = 1; h->epochA = h->epochB = 0; h->counters = nullptr; h->peer_pull = 0; h->l2_hints = 1;
-  h->tma_sin = 0; h->tmc = nullptr; h->p2block = nullptr;
+  h->tma_sin = 1; h->tmc = nullptr; h->p2block = nullptr;     // (r2k: x-adj 196 -> 192 us at 128^3, 2.11 -> 1.94 ms at 256^3)
   h->grid_acc = 1; h->accg = nullptr; h->bulk_u = 1;     // (r2e: adjoint x pass 221 -> 196 us at 128^3, 2.46 -> 2.04 ms at 256^3)
   h->push_waves = 1; h->two_streams = 0; h->err_host = nullptr; h->err_dev = nullptr;
 #if !defined(SMO_EMUL)

@@ -3,7 +3,8 @@
     python tools/sass_hist.py > profiles/r2_sass_hist.txt
 
 Shows, per kernel, the opcode counts that matter for the review: fp64 arithmetic (DFMA/DADD/DMUL), shared-memory traffic
-(LDS/STS), the staging engines (LDGSTS = 16-byte cp.async; UBLKCP = TMA bulk copy cp.async.bulk; SYNCS = mbarrier), global
+(LDS/STS), the staging engines (LDGSTS = 16-byte cp.async; UBLKCP = TMA bulk copy cp.async.bulk; UTMALDG = TMA tensor copy
+cp.async.bulk.tensor; SYNCS = mbarrier), global
 accesses, barriers and shuffles."""
 import collections
 import os
@@ -20,7 +21,7 @@ WANT = [("adjoint x pass 128^3 (XFused<Fac<16,12>, X_ADJ, GACC>)", "6XFusedINS_3
         ("y pass 128^3 inverse (FftPass<Fac<16,12>,+1,true,8>)", "7FftPassINS_3FacILi16ELi12EEELi1ELb1ELi8EEE"),
         ("SH23 adjoint, ensembles (Sh23Adj<Fac<16,16>,4,8>)", "7Sh23AdjINS_3FacILi16ELi16EEELi4ELi8EEE"),
         ("Inner_Product (VecKernel<V_DOT>)", "9VecKernelILi0EEE")]
-KEYS = ["DFMA", "DADD", "DMUL", "LDS", "STS", "LDGSTS", "UBLKCP", "SYNCS", "LDG", "STG", "CCTL", "BAR", "WARPSYNC", "SHFL", "MEMBAR", "ATOMG", "RED"]
+KEYS = ["DFMA", "DADD", "DMUL", "LDS", "STS", "LDGSTS", "UBLKCP", "UTMALDG", "SYNCS", "LDG", "STG", "CCTL", "BAR", "WARPSYNC", "SHFL", "MEMBAR", "ATOMG", "RED"]
 
 names = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", names)
