@@ -162,6 +162,10 @@ template <class K> struct LaunchCfg {
     if (v[dev] == 0) {
       if (K::SMEM > 48 * 1024)
         cudaFuncSetAttribute(smo_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+      // ask for the largest shared-memory carve-out: the occupancy query below assumes it, but without the hint the driver may
+      // pick a smaller one for kernels with modest per-CTA needs (SH23: 26 KB x 8 CTAs) - then fewer CTAs are resident than the
+      // grid was sized for and the persistent loop runs a second, partial wave (seen as launches that take 2x, r2l / r2m)
+      cudaFuncSetAttribute(smo_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
       int nb = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, smo_kernel<K>, K::THREADS, K::SMEM);
       v[dev] = nb > 0 ? nb : 1;
@@ -816,7 +820,11 @@ template <int M> struct UseHalfX { static constexpr bool value = (M == 384) || (
 template <int M> struct UseHalfX { static constexpr bool value = (M == 384); };
 #endif
 template <int M, int MODE, bool INTEG, bool GACC, bool HALF> struct XKernelOf { typedef XFused<typename FacOf<M>::type, MODE, INTEG, GACC> type; };
-template <int M, int MODE, bool INTEG, bool GACC> struct XKernelOf<M, MODE, INTEG, GACC, true> { typedef XFusedH<typename FacOf<M / 2>::type, MODE, INTEG, GACC> type; };
+#ifndef SMO_XH_T
+#define SMO_XH_T 2      // columns per CTA of the half-length x pass (2: 192-thread CTAs, two per SM; 4: one 384-thread CTA per SM);
+                        // r2m at 256^3: adjoint x pass 1.95 ms (T = 4) -> 1.81 ms (T = 2), forward 1.02 -> 1.04 ms
+#endif
+template <int M, int MODE, bool INTEG, bool GACC> struct XKernelOf<M, MODE, INTEG, GACC, true> { typedef XFusedH<typename FacOf<M / 2>::type, MODE, INTEG, GACC, SMO_XH_T> type; };
 
 template <int M> struct KdOps {
   typedef typename FacOf<M>::type F;
@@ -950,7 +958,7 @@ template <int M> struct KdOps {
   // cost "Integrated": partial-sum slots one forward step needs = sum over its z chunks of the x-pass grids (exact)
   static size_t jparts_per_step(smo_kdyn* h) {
     const int nch = yxy_chunks(h, 0);
-    XFParams p; xffill(p, h, 4, 0, nch > 1 ? h->nz / nch : -1);
+    XFParams p; xffill(p, h, XK<X_FWD, true>::T, 0, nch > 1 ? h->nz / nch : -1);
     return (size_t)nch * (size_t)grid_for<XK<X_FWD, true>>(p.nwork);
   }
   // TMA path of the spectral tiles: tensor map + slice of every input field (fields 0..2 share one array, fields 3..5 another)
@@ -970,7 +978,7 @@ template <int M> struct KdOps {
   }
   // forward: x-spectra of B (the snapshot slot or the work arrays) in, x-spectra of U x B out (work arrays)
   static int x_fwd(smo_kdyn* h, cplx* const* bp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
-    XFParams p; xffill(p, h, 4, z0, nzc);
+    XFParams p; xffill(p, h, XK<X_FWD, false>::T, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = bp2[f]; p.sout[f] = h->p2[f]; }
     tma_sources<XK<X_FWD, false>>(h, p, 3);
     int rc;
@@ -989,7 +997,7 @@ template <int M> struct KdOps {
   }
   // adjoint: x-spectra of curl G (work arrays) and of the forward state B_f (read straight from its snapshot slot) in
   static int x_adj(smo_kdyn* h, cplx* const* bfp2, rt_stream st, int z0 = 0, int nzc = -1, bool integ = false) {
-    XFParams p; xffill(p, h, 4, z0, nzc);
+    XFParams p; xffill(p, h, XK<X_ADJ, false>::T, z0, nzc);
     for (int f = 0; f < 3; ++f) { p.sin[f] = h->p2[f]; p.sout[f] = h->p2[f]; p.sin[3 + f] = bfp2[f]; }
     tma_sources<XK<X_ADJ, false, true>>(h, p, 6);
     p.accumulate = 1;
@@ -1008,7 +1016,7 @@ template <int M> struct KdOps {
   static int u_tile(smo_kdyn* h, rt_stream st) {
     UTileParams p; memset(&p, 0, sizeof p);
     for (int c = 0; c < 3; ++c) p.in[c] = h->Ug[c];
-    p.out = h->Ut; p.ncols = (long long)M * h->nz; p.M = M; p.nsteps = 1;
+    p.out = h->Ut; p.ncols = (long long)M * h->nz; p.M = M; p.nsteps = 1; p.half = HALFX ? XK<X_FWD, false>::T : 0;
     p.nwork = (int)(M * ((p.ncols + UTile::THREADS - 1) / UTile::THREADS));
     if (HALFX) return launch<UTileH>(p, st);
     return launch<UTile>(p, st);
@@ -1167,7 +1175,7 @@ template <int M> struct KdOps {
     if (h->grid_acc) {   // tile-major running sum -> grid -> x-spectra (the one r2c transform the sweep skipped)
       UTileParams u; memset(&u, 0, sizeof u);
       for (int c = 0; c < 3; ++c) u.in[c] = h->gwork + (size_t)c * h->gsize;
-      u.out = h->accg; u.ncols = (long long)M * h->nz; u.M = M; u.nsteps = 1; u.half = HALFX ? 1 : 0;
+      u.out = h->accg; u.ncols = (long long)M * h->nz; u.M = M; u.nsteps = 1; u.half = HALFX ? XK<X_FWD, false>::T : 0;
       u.nwork = (int)(M * ((u.ncols + UnTile::THREADS - 1) / UnTile::THREADS));
       TRY(launch<UnTile>(u, st));
       const double* g[3] = {h->gwork, h->gwork + h->gsize, h->gwork + 2 * h->gsize};

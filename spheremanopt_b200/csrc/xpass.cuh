@@ -577,7 +577,7 @@ struct UTileParams {
   int nwork, nsteps;
   long long ncols;
   int M;
-  int half;      // UnTile: 1 = the half-length layout of xpass_half.cuh ([ncols/4][3][M/2][4][2])
+  int half;      // 0: pair layout of XFused; T (2 or 4): the half-length layout of xpass_half.cuh ([ncols/T][3][M/2][T][2])
 };
 struct UTile {
   typedef UTileParams Params;
@@ -616,7 +616,7 @@ struct UnTile {
     if (col >= p.ncols) return;
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) {
-      const long long src = p.half ? ((((col / 4) * 3 + cc) * (p.M / 2) + n / 2) * 4 + (col % 4)) * 2 + (n & 1)
+      const long long src = p.half ? ((((col / p.half) * 3 + cc) * (p.M / 2) + n / 2) * p.half + (col % p.half)) * 2 + (n & 1)
                                    : (((col / 4) * 3 + cc) * p.M + n) * 4 + (col % 4);
       const_cast<double*>(p.in[cc])[(long long)n * p.ncols + col] = p.out[src];
     }

@@ -48,7 +48,7 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> 
   static constexpr size_t SMEM = (size_t)(SIN_ELEMS + SU_UNITS + X_ELEMS + ACC_ELEMS + 1) * sizeof(cplx);   // + the mbarrier of the velocity tile
   static_assert(R1 >= R2 && RT == R1, "the radix-R1 stage is the wide one");
   static_assert(32 % RT == 0 && FT % WT == 0 && T_ % CPW == 0, "whole FFTs per warp");
-  static_assert(T_ == 4, "the shared-memory swizzles assume 4 columns (64 bytes) per row");
+  static_assert(T_ == 2 || T_ == 4, "the shared-memory swizzles assume 2 or 4 columns (32 / 64 bytes) per row");
   static_assert(NH % 8 == 0 && H % 8 == 0 && (CPW == 2 || CPW == 4), "swizzled lines hold whole rows; blocks must start on a swizzle period");
   static_assert(NH <= H && H - NH < NH, "mode bookkeeping of the even/odd assembly");
   static_assert(MODE == X_FWD || MODE == X_ADJ, "fused modes only");
@@ -90,8 +90,11 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> 
     const int r = (f * (T / CPW) + g) * NH + row;    // row inside the stack of blocks (NH is a multiple of LROWS)
     return ((r / LROWS) << 3) + (((row % LROWS) * CPW + cc) ^ ((row / LROWS) % CPW));
   }
+  // velocity tile [3][H row pairs][T columns]: 8 / T rows per 128-byte line, same XOR swizzle idea
+  static constexpr int LROWS_U = 8 / T;
   SMO_HD static int ui(int cidx, int n, int col) {
-    return (((cidx * H + n) >> 1) << 3) + ((((n & 1) << 2) + col) ^ ((n >> 1) & 3));
+    const int r = cidx * H + n;                      // (H is a multiple of LROWS_U)
+    return ((r / LROWS_U) << 3) + (((n % LROWS_U) * T + col) ^ ((n / LROWS_U) % T));
   }
   SMO_HD static int out_field(int f) {
     if (MODE == X_FWD) return (f + 1) % 3;
@@ -317,7 +320,7 @@ template <class F, int MODE, bool INTEG = false, bool GACC = false, int T_ = 4> 
   }
 };
 
-// one-off re-layout of the velocity field for XFusedH: grid [3][M][ncols] -> [ncols/4][3][M/2][4][2]
+// one-off re-layout of the velocity field for XFusedH: grid [3][M][ncols] -> [ncols/T][3][M/2][T][2], T = p.half columns per tile
 struct UTileH {
   typedef UTileParams Params;
   static constexpr int THREADS = 256;
@@ -331,11 +334,13 @@ struct UTileH {
     const long long col = (work % per_row) * THREADS + tid;
     if (col >= p.ncols) return;
     // unit (16 bytes) = (component, row pair, column), stored at its swizzled shared-memory position XFusedH::ui()
-    const int H = p.M / 2, n2 = n / 2, cq = (int)(col % 4);
+    const int T = p.half, LR = 8 / T;
+    const int H = p.M / 2, n2 = n / 2, cq = (int)(col % T);
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) {
-      const long long unit = ((((long long)cc * H + n2) >> 1) << 3) + ((((n2 & 1) << 2) + cq) ^ ((n2 >> 1) & 3));
-      p.out[(col / 4) * (3LL * p.M * 4) + unit * 2 + (n & 1)] = p.in[cc][(long long)n * p.ncols + col];
+      const long long r = (long long)cc * H + n2;
+      const long long unit = ((r / LR) << 3) + (((n2 % LR) * T + cq) ^ ((n2 / LR) % T));
+      p.out[(col / T) * (3LL * p.M * T) + unit * 2 + (n & 1)] = p.in[cc][(long long)n * p.ncols + col];
     }
   }
 };
