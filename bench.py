@@ -502,10 +502,12 @@ def run_gpu_sh23ens(args):
     from spheremanopt_b200 import _cabi, sh23
     lib = _cabi.load()
     N, _, dt, nit = WORKLOADS[args.workload]
+    from spheremanopt_b200.ensemble import shard_slice
     total = 4096 if args.workload == "sh23ens" else world      # config 1: one instance (per GPU: replicas only)
-    nb = total // world
+    lo, hi = shard_slice(total, world, rank)
+    nb = hi - lo
     dom, X0 = sh23.Generate_IC(0.0725, N, device="cuda:%d" % local)
-    M0 = (np.linspace(0.05, 0.1, total) if args.workload == "sh23ens" else np.full(total, 0.0725))[rank * nb:(rank + 1) * nb]
+    M0 = (np.linspace(0.05, 0.1, total) if args.workload == "sh23ens" else np.full(total, 0.0725))[lo:hi]
     X = torch.from_numpy(np.sqrt(M0 / 0.0725)[:, None] * X0[None, :]).to(dom.device).reshape(-1).contiguous()
     store = sh23.GEN_BUFFER(dom, nit, N, batch=nb)
 
@@ -666,9 +668,11 @@ def run_gpu_sh23opt(args):
     N, _, dt, nit = WORKLOADS[args.workload]
     total = int(os.environ.get("SMO_ENS_TOTAL", "4096"))
     iters = int(os.environ.get("SMO_ENS_ITERS", "20"))
-    nb = total // world
+    from spheremanopt_b200.ensemble import shard_slice
+    lo, hi = shard_slice(total, world, rank)
+    nb = hi - lo
     dom, X0 = sh23.Generate_IC(0.0725, N, device="cuda:%d" % local)
-    M0 = np.linspace(0.05, 0.1, total)[rank * nb:(rank + 1) * nb]
+    M0 = np.linspace(0.05, 0.1, total)[lo:hi]
     X0s = [np.sqrt(m / 0.0725) * X0 for m in M0]
     cwd = os.getcwd()
     os.chdir(tempfile.mkdtemp())

@@ -122,6 +122,10 @@ int smo_kdyn_adjoint_host(smo_kdyn_t* h, double Rm, double dt, int n_iters, cons
                           double* gradU_host, int flags, void* stream);
 int smo_kdyn_prep_host(smo_kdyn_t* h, const double* B0_host, const double* U_host, double Rm, double dt, int n_iters,
                        double* out_host, void* stream);
+/* this rank's z-slab [3][M][M][nz] on the device <-> the full reference vector (3*M^3 doubles) on the host: one strided 2-D copy
+ * (Vec_to_Field's local slicing, KD:156-169).  Give exactly one of host_in (H2D) / host_out (D2H; only this rank's entries are
+ * written).  Asynchronous on `stream`. */
+int smo_kdyn_slab_copy(smo_kdyn_t* h, double* slab_dev, const double* host_in, double* host_out, void* stream);
 /* transform helpers (tests, initial conditions): grid [3][grid_elems] <-> coefficients [3][coef_elems] */
 int smo_kdyn_to_coef(smo_kdyn_t* h, const double* grid_dev, void* coef_dev, void* stream);
 int smo_kdyn_to_grid(smo_kdyn_t* h, const void* coef_dev, double* grid_dev, void* stream);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "smo_kdyn_forward_host": (i32, [vp, dp, dp, f64, f64, i32, vp, C.POINTER(f64), i32, vp]),
     "smo_kdyn_adjoint_host": (i32, [vp, f64, f64, i32, vp, dp, dp, i32, vp]),
     "smo_kdyn_prep_host": (i32, [vp, dp, dp, f64, f64, i32, dp, vp]),
+    "smo_kdyn_slab_copy": (i32, [vp, dp, dp, dp, vp]),
     "smo_kdyn_to_coef": (i32, [vp, dp, vp, vp]),
     "smo_kdyn_to_grid": (i32, [vp, vp, dp, vp]),
     "smo_kdyn_profile_set": (i32, [vp, i32]),

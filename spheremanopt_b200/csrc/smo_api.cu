@@ -1825,6 +1825,12 @@ static int kd_slab_copy(smo_kdyn* h, double* dev, const double* host_in, double*
   if (host_in) return rt_copy2d(dev, h->nz * sizeof(double), host_in + h->z0, M * sizeof(double), h->nz * sizeof(double), rows, 0, st);
   return rt_copy2d(host_out + h->z0, M * sizeof(double), dev, h->nz * sizeof(double), h->nz * sizeof(double), rows, 1, st);
 }
+// z-slab of this rank <-> full reference vector on the host (strided 2-D copy; the host-side numpy slicing it replaces cost
+// more than the copy itself at 8 ranks).  Exactly one of host_in / host_out is given.  Asynchronous on `stream`.
+extern "C" int smo_kdyn_slab_copy(smo_kdyn_t* h, double* slab_dev, const double* host_in, double* host_out, void* stream) {
+  if (!h || !slab_dev || (!host_in) == (!host_out)) return fail(SMO_E_ARG, "smo_kdyn_slab_copy: bad argument");
+  return kd_slab_copy(h, slab_dev, host_in, host_out, (rt_stream)stream);
+}
 extern "C" int smo_kdyn_forward_host(smo_kdyn_t* h, const double* B0, const double* U, double Rm, double dt,
                                      int n_iters, void* snaps, double* J_host, int flags, void* stream) {
   TRY(kd_args(h, Rm, dt, n_iters, flags, "smo_kdyn_forward_host"));

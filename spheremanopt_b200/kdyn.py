@@ -112,10 +112,17 @@ class Domain:
     def slab_from_host(self, x):
         """full reference vector (3*M^3) -> this rank's device slab [3][M][M][nz]"""
         M = self.M
-        a = np.asarray(x, dtype=np.float64).reshape(3, M, M, M)
-        if self.nranks > 1:
-            a = np.ascontiguousarray(a[:, :, :, self.z0:self.z0 + self.nz])
-        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=True).reshape(-1)
+        a = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        if a.size != 3 * M ** 3:
+            raise ValueError("vector of %d entries, expected 3*M^3 = %d" % (a.size, 3 * M ** 3))
+        if self.nranks == 1:
+            return torch.from_numpy(a).to(self.device, non_blocking=True)
+        # several ranks: one strided 2-D copy straight out of the caller's array (Vec_to_Field's local slicing, KD:156-169)
+        t = torch.empty(3 * self.gsize, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib, self.lib.smo_kdyn_slab_copy(self.h, t.data_ptr(), a.ctypes.data, None, _stream_ptr()))
+            torch.cuda.current_stream().synchronize()     # (`a` may be a temporary)
+        return t
 
     def host_from_slab(self, t):
         """device slab -> full reference vector on the host (all-gather over ranks, like KD:118-137)"""

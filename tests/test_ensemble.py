@@ -169,3 +169,17 @@ def test_rendezvous_scales_to_many_workers():
             want += 0.5 * (i % 4)
         assert out[i] == want
     assert R.served["f"] == sum(3 + i % 5 for i in range(K)) and calls["f"] == R.rounds["f"] < R.served["f"] / 20
+
+
+def test_shard_slice_partitions_the_ensemble():
+    """config 5's sharding: contiguous, disjoint, covering, balanced (4096 over 8 = 512 each; ragged totals differ by <= 1)"""
+    from spheremanopt_b200.ensemble import shard_slice
+    for total, world in ((4096, 8), (4096, 1), (10, 4), (3, 8), (4097, 8)):
+        parts = [shard_slice(total, world, r) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == total
+        assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_slice(4096, 8, 3) == (1536, 2048)
+    with pytest.raises(ValueError):
+        shard_slice(8, 2, 2)
