@@ -67,8 +67,8 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
 # named in NCU_SOURCE (it also reads the forward state from its snapshot slot and read-modify-writes the running sum of the
 # gradient integrand on the real grid - 340 MB that replace three r2c transforms; algorithmic model 566.2 MB)
-NCU_TRAFFIC = {("kdyn128", 1): 803.7e6}
-NCU_SOURCE = {("kdyn128", 1): "ncu --set full, build r2f (profiles/r2f_kdyn128_xadj_ncu.txt): 566.3 MB read + 237.4 MB written"}
+NCU_TRAFFIC = {("kdyn128", 1): 803.4e6}
+NCU_SOURCE = {("kdyn128", 1): "ncu --set full, build r2l (profiles/r2l_kdyn128_xpass_ncu.txt): 566.3 MB read + 237.1 MB written"}
 METRIC = "Grad_f evals/s (fwd+adjoint)"
 UNIT = "Grad_f evals/s"
 # fp64 work of one SH23 instance pair (~138 GFLOP per 4096-instance pair at N_ITERS = 500): per time step one
