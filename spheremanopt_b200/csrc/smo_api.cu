@@ -834,7 +834,10 @@ template <int M> struct KdOps {
   static constexpr int TY = SMO_TY;    // lines per CTA, strided (y) passes
   static constexpr int TX = SMO_TX;    // columns per CTA, x passes with <= 3 fields
   static constexpr int TXA = SMO_TXA;  // columns per CTA, fused adjoint x pass (6 fields)
-  static constexpr int TZS = SMO_TZS;  // lines per CTA (x 3 components), fused z step
+#ifndef SMO_TZS_WIDE
+#define SMO_TZS_WIDE SMO_TZS    // ... for grids whose z FFT needs 24 stage threads (M = 384): CTA-wide barriers, so smaller CTAs may pay
+#endif
+  static constexpr int TZS = (FacOf<M>::type::RT > 16) ? SMO_TZS_WIDE : SMO_TZS;  // lines per CTA (x 3 components), fused z step
 
   static void fill(PassParams& p, smo_kdyn* h, int nf) {
     memset(&p, 0, sizeof p);
