@@ -58,10 +58,13 @@ template <class F, int T_> struct ZStep {
   static constexpr bool V2 = true;
   static constexpr int T = T_, M = F::M, R1 = F::R1, R2 = F::R2, RT = F::RT, XP = F::XP;
   static constexpr int KMAX = M / 3 - 1, NC = 2 * KMAX + 1, PC = NC + 1;
-  static constexpr int THREADS = 3 * T_ * F::RT;
+  // lanes reserved per line: RT, or a whole warp when RT does not divide 32 (384 = 24 x 16: 24 stage threads) - a line is then
+  // private to one warp (8 idle lanes in the FFT stages, all 32 in the copies) and the warp-level barriers apply
+  static constexpr int LP = (F::RT > 16 && F::RT < 32) ? 32 : F::RT;
+  static constexpr int THREADS = 3 * T_ * LP;
   static constexpr int NPHASES = 9;
   static constexpr int MIN_BLOCKS = (F::RT > 16) ? 2 : SMO_ZS_MB;
-  static constexpr bool WARP_OK = (32 % F::RT == 0);       // the RT threads of a line never straddle a warp
+  static constexpr bool WARP_OK = (32 % LP == 0);          // the threads of a line never straddle a warp
   static constexpr int LAND = 3 * T_ * M, WORK = 3 * T_ * XP, STATE = 3 * T_ * PC;
   static constexpr size_t SMEM = (size_t)(LAND + WORK + STATE + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int) + 16;
   static_assert(XP >= PC, "compact coefficient line must fit into the exchange line");
@@ -81,9 +84,9 @@ template <class F, int T_> struct ZStep {
   SMO_HD static unsigned long long* pols(unsigned char* s) { return reinterpret_cast<unsigned long long*>(segrem(s) + M); }
 
   SMO_HD static void split_tid(int tid, int& f, int& t, int& jj) {
-    jj = tid % RT;
-    t = (tid / RT) % T;
-    f = tid / (RT * T);
+    jj = tid % LP;
+    t = (tid / LP) % T;
+    f = tid / (LP * T);
   }
   SMO_HD static void decode(const Params& p, int work, int& tile, int& trip) {
     tile = work / p.ntrip;
@@ -100,18 +103,18 @@ template <class F, int T_> struct ZStep {
     const cplx* src = p.in[3 * trip + f] + (long long)b * p.line_stride;
     if (p.seglen <= 0 && p.l2_hints) {
       const unsigned long long pol = pols(c.smem)[0];
-      for (int e = jj; e < M; e += RT) cp_async16_hint(&Ld[e], src + e, pol);
+      for (int e = jj; e < M; e += LP) cp_async16_hint(&Ld[e], src + e, pol);
     } else if (p.seglen <= 0) {
-      for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], src + e);
+      for (int e = jj; e < M; e += LP) cp_async16(&Ld[e], src + e);
     } else if (p.pull_mode == 1) {
       const int* si = segidx(c.smem);
       const int* sr = segrem(c.smem);
       const long long line = p.pull_off + (long long)b * p.line_stride;
-      for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], p.peer_in[3 * trip + f][si[e]] + line + sr[e]);
+      for (int e = jj; e < M; e += LP) cp_async16(&Ld[e], p.peer_in[3 * trip + f][si[e]] + line + sr[e]);
     } else {
       const int* si = segidx(c.smem);
       const int* sr = segrem(c.smem);
-      for (int e = jj; e < M; e += RT) cp_async16(&Ld[e], src + (long long)si[e] * p.blk + sr[e]);
+      for (int e = jj; e < M; e += LP) cp_async16(&Ld[e], src + (long long)si[e] * p.blk + sr[e]);
     }
   }
 
@@ -127,9 +130,9 @@ template <class F, int T_> struct ZStep {
     const cplx* src = p.b[3 * trip + f] + (long long)b * p.Pc;
     if (p.l2_hints) {
       const unsigned long long pol = pols(c.smem)[0];
-      for (int e = jj; e < PC; e += RT) cp_async16_hint(&Sd[e], src + e, pol);
+      for (int e = jj; e < PC; e += LP) cp_async16_hint(&Sd[e], src + e, pol);
     } else {
-      for (int e = jj; e < PC; e += RT) cp_async16(&Sd[e], src + e);
+      for (int e = jj; e < PC; e += LP) cp_async16(&Sd[e], src + e);
     }
   }
   SMO_HD static void init(const Params& p, const Ctx& c, State& st) {
