@@ -200,7 +200,8 @@ int smo_vec_dot(const double* x_dev, const double* y_dev, long long n, double sc
                 void* work_dev, void* stream);
 /* the same without the D2H copy / synchronisation: the scaled sum is left in ((double*)work_dev)[0] */
 int smo_vec_dot_dev(const double* x_dev, const double* y_dev, long long n, double scale, void* work_dev, void* stream);
-/* batched form for many short vectors (ensembles): out_dev[r] = scale * sum_j x[r][j]*y[r][j], r < rows; one launch, no sync */
+/* batched form of Inner_Prod (SH:158-172) for many short vectors (ensembles of SH23 problems):
+ * out_dev[r] = scale * sum_j x[r][j]*y[r][j], r < rows; one launch, no sync */
 int smo_vec_dot_rows(const double* x_dev, const double* y_dev, int rows, long long len, double scale, double* out_dev, void* stream);
 /* 64-bit position-sensitive checksum of the bit patterns of x (sum_i bits(x_i)*(2i+1) mod 2^64): the host layer's identity check
  * of the X a snapshot store was filled for (the f -> Grad_f coupling of SGD:740-796).  Synchronises the stream. */

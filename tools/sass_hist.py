@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "spheremanopt_b200", "libsmo_b200.so")
 WANT = [("adjoint x pass 128^3 (XFused<Fac<16,12>, X_ADJ, GACC>)", "6XFusedINS_3FacILi16ELi12EEELi3ELb0ELb1EEE"),
         ("forward x pass 128^3 (XFused<Fac<16,12>, X_FWD>)", "6XFusedINS_3FacILi16ELi12EEELi2ELb0ELb0EEE"),
-        ("adjoint x pass 256^3 (XFusedH<Fac<16,12>, X_ADJ, GACC>)", "7XFusedHINS_3FacILi16ELi12EEELi3ELb0ELb1ELi4EEE"),
+        ("adjoint x pass 256^3 (XFusedH<Fac<16,12>, X_ADJ, GACC>)", "7XFusedHINS_3FacILi16ELi12EEELi3ELb0ELb1ELi2EEE"),
         ("fused z step 128^3 (ZStep<Fac<16,12>,2>)", "5ZStepINS_3FacILi16ELi12EEELi2EEE"),
         ("y pass 128^3 inverse (FftPass<Fac<16,12>,+1,true,8>)", "7FftPassINS_3FacILi16ELi12EEELi1ELb1ELi8EEE"),
         ("SH23 adjoint, ensembles (Sh23Adj<Fac<16,16>,4,8>)", "7Sh23AdjINS_3FacILi16ELi16EEELi4ELi8EEE"),
