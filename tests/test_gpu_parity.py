@@ -278,34 +278,40 @@ def test_devvec_and_sphere_ops():
     assert relerr(u, osp.Update_vector(x, 0.7, d, 2.5, okd.Inner_Prod_3, (od,))) <= 1e-13
 
 
-def test_bitwise_reproducible_runs():
-    """the warp-synchronous kernels (one FFT line / field / instance per warp, __syncwarp instead of CTA barriers; only
-    active for 16 stage threads, i.e. the 128^3 dynamo and SH23) give bit-identical results run after run - a missing
-    barrier would show up as run-to-run noise"""
+@pytest.mark.parametrize("Npts", [128, 256])
+def test_bitwise_reproducible_runs(Npts):
+    """the warp-synchronous kernels (one FFT line / field / instance per warp, __syncwarp instead of CTA barriers; TMA copies
+    waited on with mbarriers) give bit-identical results run after run - a missing barrier or an early read of a tile still in
+    flight would show up as run-to-run noise.  128^3: pair-packed x pass; 256^3: half-length x pass + one-line-per-warp z step.
+    (compute-sanitizer's racecheck is not available on this pool.)"""
     import torch
     from spheremanopt_b200 import kdyn, sh23
     from spheremanopt_b200.devvec import DevVec
-    dom = kdyn.Domain(128)
+    dom = kdyn.Domain(Npts)
     g = torch.Generator(device="cpu").manual_seed(11)
     X = [DevVec(torch.randn(3 * dom.M ** 3, dtype=torch.float64, generator=g).to(dom.device)) for _ in range(2)]
-    st = kdyn.GEN_BUFFER(128, dom, 3, checkpoint_every=0)
+    nit = 3 if Npts == 128 else 2
+    st = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=0)
     runs = []
     for rep in range(3):
-        f = kdyn.FWD_Solve_IVP_Lin(X, dom, 10.0, 1e-3, 3, 3, st)
-        gr = kdyn.ADJ_Solve_IVP_Lin(X, dom, 10.0, 1e-3, 3, 3, st)
+        f = kdyn.FWD_Solve_IVP_Lin(X, dom, 10.0, 1e-3, nit, nit, st)
+        gr = kdyn.ADJ_Solve_IVP_Lin(X, dom, 10.0, 1e-3, nit, nit, st)
         runs.append((f, gr[0].t.clone(), gr[1].t.clone()))
     for r in runs[1:]:
         assert r[0] == runs[0][0] and torch.equal(r[1], runs[0][1]) and torch.equal(r[2], runs[0][2])
+    if Npts != 128:
+        return
     sd = sh23.Domain(256)
-    Xs = (torch.randn(37 * sd.M, dtype=torch.float64, generator=g) * 0.05).to(sd.device)
-    ss = sh23.GEN_BUFFER(sd, 50, batch=37)
-    ref = None
-    for rep in range(3):
-        J = sh23.forward_batch(Xs, sd, 0.1, 50, ss).clone()
-        G = sh23.adjoint_batch(sd, 0.1, 50, ss).clone()
-        if ref is None:
-            ref = (J, G)
-        assert torch.equal(J, ref[0]) and torch.equal(G, ref[1])
+    for batch in (37, 1300):        # few-instance (latency) variant and ensemble variant (8 CTAs per SM) of the SH23 kernels
+        Xs = (torch.randn(batch * sd.M, dtype=torch.float64, generator=g) * 0.05).to(sd.device)
+        ss = sh23.GEN_BUFFER(sd, 50, batch=batch)
+        ref = None
+        for rep in range(3):
+            J = sh23.forward_batch(Xs, sd, 0.1, 50, ss).clone()
+            G = sh23.adjoint_batch(sd, 0.1, 50, ss).clone()
+            if ref is None:
+                ref = (J, G)
+            assert torch.equal(J, ref[0]) and torch.equal(G, ref[1])
 
 
 def test_c_abi_host_entry_points():

@@ -24,5 +24,11 @@ Xs = torch.randn(6 * sd.M, dtype=torch.float64, device="cuda", generator=g) * 0.
 ss = sh23.GEN_BUFFER(sd, 3, batch=6)
 J = sh23.forward_batch(Xs, sd, 0.1, 3, ss)
 G = sh23.adjoint_batch(sd, 0.1, 3, ss)
+# the ensemble variant of the SH23 kernels (more than 2*148 CTAs: 128-register build, 8 CTAs per SM)
+nb = 1300
+Xe = torch.randn(nb * sd.M, dtype=torch.float64, device="cuda", generator=g) * 0.05
+se = sh23.GEN_BUFFER(sd, 3, batch=nb)
+Je = sh23.forward_batch(Xe, sd, 0.1, 3, se)
+Ge = sh23.adjoint_batch(sd, 0.1, 3, se)
 torch.cuda.synchronize()
-print("ok", f, fi, float(J.sum()), float(G.abs().sum()))
+print("ok", f, fi, float(J.sum()), float(G.abs().sum()), float(Je.sum()), float(Ge.abs().sum()))
