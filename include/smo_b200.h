@@ -174,6 +174,14 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
  * row pitch of the x-spectral arrays) with TMA tensor copies (cp.async.bulk.tensor, 3-D tiled maps with hardware swizzle,
  * one copy per field and tile) instead of 16-byte cp.async copies; 0 = cp.async. */
 #define SMO_OPT_TMA_SIN 9
+/* SMO_OPT_PDL: 1 = inside the time loops of a single-rank handle every kernel is launched with programmatic stream
+ * serialisation (programmatic dependent launch): the CTAs of launch n+1 become resident and run their prologue (shared-memory
+ * set-up, mbarrier initialisation, twiddle tables) while the last CTAs of launch n drain, and block in griddepcontrol.wait until
+ * launch n has completed and flushed.  Captured into the CUDA graphs as programmatic edges; results are bit-identical.
+ * 0 = plain stream order; -1 (default) = automatic: on for Npts <= 64 (launch-latency-bound steps: -16 % at 16^3, -10 % at 24^3,
+ * -7 % at 32^3), off above (measured 5 % slower at 128^3 and 256^3).  Always off with several ranks, two streams or per-kernel
+ * profiling events. */
+#define SMO_OPT_PDL 10
 int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);

@@ -89,6 +89,7 @@ SMO_OPT_TWO_STREAMS = 6
 SMO_OPT_GRID_ACC = 7
 SMO_OPT_BULK_U = 8
 SMO_OPT_TMA_SIN = 9
+SMO_OPT_PDL = 10
 
 
 def bind(cdll):

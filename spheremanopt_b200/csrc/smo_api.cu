@@ -69,6 +69,16 @@ using namespace smo;
 // ------------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+// set by the time loops of a single-rank handle (PdlScope): launches carry the programmatic-stream-serialisation attribute
+static thread_local int t_pdl = 0;
+struct PdlScope {
+  int old;
+  explicit PdlScope(int on) : old(t_pdl) { t_pdl = on; }
+  ~PdlScope() { t_pdl = old; }
+};
+#ifndef SMO_PDL_DEFAULT
+#define SMO_PDL_DEFAULT -1
+#endif
 
 static int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -187,7 +197,19 @@ template <class K> static int launch(const typename K::Params& p, rt_stream st, 
     const int g2 = (p.nwork + waves - 1) / waves;
     if (g2 < grid) grid = g2 > 0 ? g2 : 1;
   }
-  smo_kernel<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+  if (t_pdl) {
+    // programmatic dependent launch: this grid may become resident while its predecessor in the stream drains; smo_kernel blocks
+    // in griddepcontrol.wait before it touches anything the predecessor wrote (SMO_OPT_PDL)
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)K::THREADS); cfg.dynamicSmemBytes = K::SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, smo_kernel<K>, p);
+    if (e != cudaSuccess) return fail(SMO_E_CUDA, "cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
+  } else {
+    smo_kernel<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+  }
   g_launches++;
   return rt_check("kernel launch");
 }
@@ -566,6 +588,7 @@ struct smo_kdyn {
   int tma_sin;                  // 1: ... and their spectral tiles with TMA tensor copies (tensor maps cached per source array)
   struct TmCache* tmc;          // registered x-spectral arrays (work block, snapshot store, checkpoint segment) and their tensor maps
   cplx* p2block;                // the six y-padded work arrays are one allocation (one tensor map, slice = field)
+  int pdl;                      // 1: programmatic dependent launches inside the single-rank time loops (SMO_OPT_PDL)
   int grid_acc; double* accg;   // 1: the adjoint x pass sums (curl G) x B_f on the real grid (tile-major, 3*gsize doubles) instead of on the x-spectra
   int push_waves;               // pushing kernels run ~push_waves work items per CTA so that remote stores drain under compute
   int two_streams;              // 1: the z chunks of the y -> x -> y section alternate between two streams (transfers of one
@@ -1258,8 +1281,15 @@ template <class Body> static int run_graphed(smo_kdyn* h, const GraphKey& key, r
   return 0;
 #endif
 }
+// programmatic dependent launches: only where every launch of the loop is a smo_kernel on ONE stream of ONE rank.  -1 (default) =
+// automatic: on for the small grids, whose steps are launch-latency bound (B200, r2z: 16^3 -16 %, 24^3 -10.5 %, 32^3 -7 %, 64^3 -1.5 %
+// per Grad_f pair), off for the large ones, where CTAs that move in early make the kernels 5 % slower (128^3, 256^3)
+static int pdl_on(const smo_kdyn* h) {
+  if (h->nranks != 1 || h->two_streams != 0 || h->prof_which != 0) return 0;
+  return h->pdl < 0 ? (h->N <= 64 ? 1 : 0) : (h->pdl ? 1 : 0);
+}
 static int graph_opts(const smo_kdyn* h) {
-  return ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
+  return (pdl_on(h) ? (int)(1u << 31) : 0) | ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
          ((h->two_streams & 1) ? 16 : 0) | ((h->two_streams & 2) ? (1 << 29) : 0) | ((h->push_waves & 3) << 5) | (h->grid_acc ? 128 : 0) | (h->bulk_u ? (1 << 28) : 0) | (h->tma_sin ? (1 << 30) : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
 }
 
@@ -1311,6 +1341,7 @@ static int kd_forward_loop(smo_kdyn* h, int n_steps, bool tail_xs_only, double R
   key.p2 = first.cin[0]; key.Rm = Rm; key.dt = dt; key.hsh = 0;
   for (int n = 0; n < n_steps; ++n) { const FwdStep b = step(n); key.hsh = hash_ptr(hash_ptr(hash_ptr(key.hsh, b.cin[0]), b.cout[0]), b.xs[0]); }
   return run_graphed(h, key, st, [&](rt_stream s) -> int {
+    PdlScope pdl(pdl_on(h));
     TRY(KdOps<M>::inv_z(h, first.cin, h->p1, 3, s, XS_B));
     if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, s));
     for (int n = 0; n < n_steps; ++n) {
@@ -1400,6 +1431,7 @@ static int kd_adjoint_loop(smo_kdyn* h, int count, double Rm, double dt, StateFn
   GraphKey key; key.kind = integ ? 12 : 2; key.n = count; key.opts = graph_opts(h); key.p0 = state(0).p[0]; key.p1 = state(count - 1).p[0]; key.p2 = nullptr; key.Rm = Rm; key.dt = dt; key.hsh = 0;
   for (int i = 0; i < count; ++i) key.hsh = hash_ptr(key.hsh, state(i).p[0]);
   return run_graphed(h, key, st, [&](rt_stream q) -> int {
+    PdlScope pdl(pdl_on(h));
     TRY(KdOps<M>::inv_z(h, h->W, h->p1, 3, q, XS_B));
     if (!ks) TRY(a2a(h, h->p1, h->p1t, 3, q));
     for (int i = 0; i < count; ++i) {
@@ -1558,6 +1590,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->tma_sin = 1; h->tmc = nullptr; h->p2block = nullptr;     // (r2k: x-adj 196 -> 192 us at 128^3, 2.11 -> 1.94 ms at 256^3)
   h->grid_acc = 1; h->accg = nullptr; h->bulk_u = 1;     // (r2e: adjoint x pass 221 -> 196 us at 128^3, 2.46 -> 2.04 ms at 256^3)
   h->push_waves = 1; h->two_streams = 0; h->err_host = nullptr; h->err_dev = nullptr;
+  h->pdl = SMO_PDL_DEFAULT;
 #if !defined(SMO_EMUL)
   h->aux_stream = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
 #endif
@@ -1789,6 +1822,7 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
     case SMO_OPT_GRID_ACC: h->grid_acc = value ? 1 : 0; return 0;
     case SMO_OPT_BULK_U: h->bulk_u = value ? 1 : 0; return 0;
     case SMO_OPT_TMA_SIN: h->tma_sin = value ? 1 : 0; return 0;
+    case SMO_OPT_PDL: h->pdl = value < 0 ? -1 : (value ? 1 : 0); return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic
       for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) { h->peer_p1[f][s2] = h->p1[f]; h->peer_p1t[f][s2] = h->p1t[f]; }
       return 0;

@@ -297,6 +297,19 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const __grid_constant__ typename K::Params p) {
   extern __shared__ __align__(1024) unsigned char smo_smem[];     // (TMA swizzle patterns are functions of the shared-memory address)
   typename K::State st;
+  if constexpr (is_v2<K>::value) {
+    Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
+    K::init(p, c, st);
+    __syncthreads();
+  }
+  // Programmatic dependent launch (SMO_OPT_PDL): when the launch carries the programmatic-stream-serialisation attribute this CTA
+  // may have started while the previous kernel of the stream was still draining.  Everything above touched only kernel parameters,
+  // constant tables and shared memory; from here on the kernel reads and writes what its predecessor produced, so wait until that
+  // grid has completed and its stores are visible - then let the NEXT kernel's CTAs move in as ours exit.  Both instructions are
+  // no-ops for a launch without the attribute.  (Measured, r2z: triggering only after the work loop gains nothing at any size; an
+  // explicit start stagger of the co-resident CTAs changes nothing either.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if constexpr (has_xsync<K>::value) {
     if (p.xs.wait_flags != nullptr) {
       if ((int)threadIdx.x < p.xs.wait_n) {
@@ -305,11 +318,6 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const __
       }
       __syncthreads();
     }
-  }
-  if constexpr (is_v2<K>::value) {
-    Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
-    K::init(p, c, st);
-    __syncthreads();
   }
   for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
     for (int step = 0; step < p.nsteps; ++step)

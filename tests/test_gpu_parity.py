@@ -203,6 +203,37 @@ def test_kdyn_graph_replay():
         assert fc == f0 and np.array_equal(gc[0], g0[0]) and np.array_equal(gc[1], g0[1])
 
 
+@pytest.mark.parametrize("Npts,nit", [(24, 40), (64, 6)])
+def test_kdyn_programmatic_dependent_launch_is_bitwise_neutral(Npts, nit):
+    """SMO_OPT_PDL: the kernels of the time loops are launched with programmatic stream serialisation (the next kernel's CTAs
+    move in while the previous one drains and block in griddepcontrol.wait); eagerly and from the CUDA graphs, with stored and
+    checkpointed sweeps, the results are bit-identical to plain stream order - and equal to the oracle."""
+    from spheremanopt_b200 import kdyn, _cabi
+    dom = kdyn.Domain(Npts)
+    od = okd.domain_kdyn(Npts)
+    B0, U = kdyn_field(od, 1), kdyn_field(od, 2)
+    res = {}
+    for pdl in (0, 1):
+        assert dom.lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_PDL, pdl) == 0
+        for graph in (0, 1):
+            dom.lib.smo_kdyn_use_graph(dom.h, graph)
+            for every in (0, 7):
+                store = kdyn.GEN_BUFFER(Npts, dom, nit, checkpoint_every=every)
+                for rep in range(3 if graph else 1):      # eager, capture, replay
+                    f = kdyn.FWD_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, store)
+                    g = kdyn.ADJ_Solve_IVP_Lin([B0, U], dom, 1.0, 1e-3, nit, nit, store)
+                    res[(pdl, graph, every, rep)] = (f, g[0].copy(), g[1].copy())
+    f0, gb0, gu0 = res[(0, 0, 0, 0)]
+    for key, (f, gb, gu) in res.items():
+        assert f == f0 and np.array_equal(gb, gb0) and np.array_equal(gu, gu0), key
+    if Npts == 24:
+        obuf = okd.GEN_BUFFER(Npts, od, nit)
+        fo = okd.FWD_Solve_IVP_Lin([B0, U], od, 1.0, 1e-3, nit, nit, obuf)
+        go = okd.ADJ_Solve_IVP_Lin([B0, U], od, 1.0, 1e-3, nit, nit, obuf)
+        assert abs(f0 - fo) <= 1e-9 * abs(fo)                     # tolerance of north_star: 1e-9 relative
+        assert relerr(gb0, go[0]) <= 1e-9 and relerr(gu0, go[1]) <= 1e-9
+
+
 @pytest.mark.parametrize("Npts,nit,adj,every", [(24, 12, "Discrete", 0), (32, 6, "Continuous", 0), (24, 12, "Discrete", 5)])
 def test_kdyn_integrated_cost(Npts, nit, adj, every):
     """Cost_function="Integrated" (KD:655-669, 738-742, 861-864), stored and checkpointed sweeps"""

@@ -43,7 +43,7 @@ for _ in range(3):
 for cf, ca in chunk_sets:
   lib.smo_kdyn_set_chunks(dom.h, cf, ca)
   print("chunks fwd/adj:", cf, ca)
-  for which in ((0, 1, 2, 3, 6, 4, 7) if len(chunk_sets) == 1 else (0,)):
+  for which in ((0, 1, 2, 3, 6, 4, 7) if len(chunk_sets) == 1 and not os.environ.get("TOTAL_ONLY") else (0,) * int(os.environ.get("TOTAL_ONLY") or 1)):
     for fn, nm, alg in ((kdyn.FWD_Solve_IVP_Lin, "fwd", alg_f), (kdyn.ADJ_Solve_IVP_Lin, "adj", alg_a)):
         lib.smo_kdyn_profile_set(dom.h, which)
         torch.cuda.synchronize(); t = time.time()
