@@ -182,6 +182,11 @@ int smo_kdyn_set_chunks(smo_kdyn_t* h, int chunks_fwd, int chunks_adj);
  * -7 % at 32^3), off above (measured 5 % slower at 128^3 and 256^3).  Always off with several ranks, two streams or per-kernel
  * profiling events. */
 #define SMO_OPT_PDL 10
+/* SMO_OPT_BULK_PUSH: peer-memory transposes of the time loops (push mode) through the TMA: the results are staged in shared memory
+ * and shipped to their owner with bulk stores (cp.async.bulk.global.shared::cta) instead of 16-byte stores from every thread, so that
+ * remote stores do not queue in the SM's load/store path in front of the local loads.  bit 0 = fused z step (one store per warp and
+ * peer), bit 1 = forward y pass (one store per truncated row). */
+#define SMO_OPT_BULK_PUSH 11
 int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value);
 /* capture each time loop into a CUDA graph and replay it (launch-bound small grids); 0 = off (default) */
 int smo_kdyn_use_graph(smo_kdyn_t* h, int on);

@@ -90,6 +90,7 @@ SMO_OPT_GRID_ACC = 7
 SMO_OPT_BULK_U = 8
 SMO_OPT_TMA_SIN = 9
 SMO_OPT_PDL = 10
+SMO_OPT_BULK_PUSH = 11
 
 
 def bind(cdll):

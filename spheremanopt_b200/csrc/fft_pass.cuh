@@ -61,15 +61,19 @@ struct PassParams {
   XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
   int hint_in, hint_out;    // L2 residency hints of the loads / stores (0 none, 1 evict_first, 2 evict_last; y passes only)
 };
+// STAGE (forward y pass with peer_mode 2 only): the truncated result tile [NC rows][T columns] is staged in shared memory (in
+// place of the consumed exchange buffer) and shipped to the row's owner with TMA bulk stores (one 16*T-byte row each, issued by
+// the lanes of warp 0) instead of 16-byte stores from every thread: the remote traffic leaves the LSU path of the SM.
 
-template <class F, int DIR, bool TFAST, int T_> struct FftPass {
+template <class F, int DIR, bool TFAST, int T_, bool STAGE = false> struct FftPass {
   typedef PassParams Params;
   static constexpr bool V2 = true;
   static constexpr bool PAD = DIR > 0;   // inverse direction: compact input, full-length output
   static constexpr int T = T_, M = F::M, R1 = F::R1, R2 = F::R2, RT = F::RT;
   static constexpr int KMAX = M / 3 - 1, NC = 2 * KMAX + 1;      // dealias 3/2: Npts = 2M/3, kmax = Npts/2 - 1
   static constexpr int THREADS = T_ * F::RT;
-  static constexpr int NPHASES = 4;
+  static constexpr int NPHASES = STAGE ? 6 : 4;
+  static_assert(!STAGE || (TFAST && DIR < 0), "staged push: forward y pass only");
   static constexpr int MIN_BLOCKS = (F::RT > 16) ? 2 : ((T_ * F::RT <= 64) ? 2 * SMO_PASS_MB : SMO_PASS_MB);   // RT > 16: 48+ doubles per thread
   // input tile: y pass [rows][T]; z pass [T][LENP]
   static constexpr int NIN = PAD ? NC : M;
@@ -173,11 +177,23 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
     if (PH == 0) {
       // (first tile of this CTA: start its own stream;) prefetch the next tile of this CTA into the other buffer,
       // then wait for the current one
-      if (st.it == 0) { load_tile(p, work, cur, c); cp_async_commit(); }
-      if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, cur ^ 1, c);
-      cp_async_commit();
-      cp_async_wait<1>();
+      if (STAGE) {
+        // the other buffer was the staging area of the previous tile: its bulk stores must have read it before the prefetch
+        // (issued in phase 1, after the barrier) may overwrite it
+        if (st.it == 0) { load_tile(p, work, cur, c); cp_async_commit(); }
+        if (c.tid < 32) bulk_wait_read();
+        cp_async_wait<0>();
+      } else {
+        if (st.it == 0) { load_tile(p, work, cur, c); cp_async_commit(); }
+        if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, cur ^ 1, c);
+        cp_async_commit();
+        cp_async_wait<1>();
+      }
     } else if (PH == 1) {
+      if (STAGE) {
+        if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, cur ^ 1, c);
+        cp_async_commit();
+      }
       if (jj < R2) {
         const int j = jj;
 #pragma unroll
@@ -208,7 +224,7 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) B[xidx(t, jj * F::SK + k1)] = make_double2(st.re[k1], st.im[k1]);
       }
-    } else {
+    } else if (PH == 3) {
       if (jj < R1) {
         const int k1 = jj;
 #pragma unroll
@@ -220,7 +236,9 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
         int f, a, bt;
         decode(p, work, f, a, bt);
         const int b = bt * T + t;
-        if (b < p.nB) {
+        if (STAGE) {
+          // results stay in registers until every thread has read the exchange buffer (barrier), phases 4 / 5 ship them
+        } else if (b < p.nB) {
           if (PAD && !TFAST && p.peer_mode == 1) {
             const long long line = p.peer_off + (long long)(p.b0 + b) * p.out_sB;
 #pragma unroll
@@ -234,7 +252,13 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
               dst = p.peer_out[f][a / p.peer_rows] + p.peer_off + (long long)(a % p.peer_rows) * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
             else
               dst = p.out[f] + (long long)a * p.out_sA + (long long)(p.b0 + b) * p.out_sB;
-            if (p.hint_out) {
+            if (!PAD && TFAST && p.peer_mode == 2) {
+#pragma unroll
+              for (int k2 = 0; k2 < R2; ++k2) {
+                const int off = st.ooff[k2];
+                if (off >= 0) st_peer(dst + off, st.re[k2] * p.scale, st.im[k2] * p.scale);
+              }
+            } else if (p.hint_out) {
               const unsigned long long pol = pols(c.smem)[1];
 #pragma unroll
               for (int k2 = 0; k2 < R2; ++k2) {
@@ -250,6 +274,27 @@ template <class F, int DIR, bool TFAST, int T_> struct FftPass {
             }
           }
         }
+      }
+      if (!STAGE) st.it++;
+    }
+    if (STAGE && PH == 4) {
+      // truncated, scaled results -> staging tile [compact row][T] in the consumed exchange buffer
+      if (jj < R1) {
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+          const int cidx = compact_index(jj + R1 * k2, M, KMAX);
+          if (cidx >= 0) B[cidx * T + t] = make_double2(st.re[k2] * p.scale, st.im[k2] * p.scale);
+        }
+      }
+      bulk_fence_smem();
+    }
+    if (STAGE && PH == 5) {
+      if (c.tid < 32) {
+        int f, a, bt;
+        decode(p, work, f, a, bt);
+        cplx* dst = p.peer_out[f][a / p.peer_rows] + p.peer_off + (long long)(a % p.peer_rows) * p.out_sA + (long long)(p.b0 + bt * T) * p.out_sB;
+        for (int row = c.tid; row < NC; row += 32) bulk_store(dst + (long long)row * p.out_sN, &B[row * T], (unsigned)(T * sizeof(cplx)));
+        bulk_commit();
       }
       st.it++;
     }

@@ -76,6 +76,9 @@ struct PdlScope {
   explicit PdlScope(int on) : old(t_pdl) { t_pdl = on; }
   ~PdlScope() { t_pdl = old; }
 };
+#ifndef SMO_BULK_PUSH_DEFAULT
+#define SMO_BULK_PUSH_DEFAULT 0
+#endif
 #ifndef SMO_PDL_DEFAULT
 #define SMO_PDL_DEFAULT -1
 #endif
@@ -588,6 +591,7 @@ struct smo_kdyn {
   int tma_sin;                  // 1: ... and their spectral tiles with TMA tensor copies (tensor maps cached per source array)
   struct TmCache* tmc;          // registered x-spectral arrays (work block, snapshot store, checkpoint segment) and their tensor maps
   cplx* p2block;                // the six y-padded work arrays are one allocation (one tensor map, slice = field)
+  int bulk_push;                // peer-memory pushes through TMA bulk stores of staged blocks: bit 0 = fused z step, bit 1 = forward y pass
   int pdl;                      // 1: programmatic dependent launches inside the single-rank time loops (SMO_OPT_PDL)
   int grid_acc; double* accg;   // 1: the adjoint x pass sums (curl G) x B_f on the real grid (tile-major, 3*gsize doubles) instead of on the x-spectra
   int push_waves;               // pushing kernels run ~push_waves work items per CTA so that remote stores drain under compute
@@ -730,7 +734,7 @@ static int a2a(smo_kdyn* h, cplx* const* src, cplx* const* dst, int nf, rt_strea
 // hsh = hash over EVERY buffer pointer the steps of the loop touch (checkpoint slots depend on `every`, which the first /
 // last pointers alone do not pin down: two CheckpointStores of equal size but different spacing must not share a graph)
 struct GraphKey {
-  int kind, n, opts; const void* p0; const void* p1; const void* p2; double Rm, dt; unsigned long long hsh;
+  int kind, n; long long opts; const void* p0; const void* p1; const void* p2; double Rm, dt; unsigned long long hsh;
   bool operator==(const GraphKey& o) const {
     return kind == o.kind && n == o.n && opts == o.opts && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 && Rm == o.Rm && dt == o.dt && hsh == o.hsh;
   }
@@ -752,6 +756,7 @@ enum { XS_NONE = 0, XS_A = 1, XS_B = 2 };
 static bool kernel_sync(const smo_kdyn* h) { return h->peer_on && h->inkernel_sync; }
 // the launch about to be issued publishes "buffer `which` (z chunk `chunk`) of every peer is filled by this rank" when it has
 // finished.  Epochs: one per transpose (all chunks of one transpose carry the same epoch; xs_next_epoch starts a new one).
+static int g_trace_n = 0;     // launch numbering of the development time-stamp trace (-DSMO_XS_TRACE)
 static unsigned long long xs_next_epoch(smo_kdyn* h, int which) { return (which == XS_A) ? ++h->epochA : ++h->epochB; }
 static void xs_signal(smo_kdyn* h, XSync& xs, int which, int chunk = 0, unsigned long long epoch = 0) {
   if (which == XS_NONE || !kernel_sync(h)) return;
@@ -761,6 +766,7 @@ static void xs_signal(smo_kdyn* h, XSync& xs, int which, int chunk = 0, unsigned
   for (int s = 0; s < h->nranks; ++s) xs.sig_flags[s] = h->peer_flags[s] + (which * MAXCH + chunk) * MAXP;
   xs.counter = h->counters + which * MAXCH + chunk;
   xs.err = h->err_dev;
+  if (!xs.trace_id) xs.trace_id = ++g_trace_n;
 }
 // the launch about to be issued first waits for the latest signal `which` (all `nch` chunks of it) of every rank
 static void xs_wait(smo_kdyn* h, XSync& xs, int which, int nch = 1) {
@@ -769,7 +775,16 @@ static void xs_wait(smo_kdyn* h, XSync& xs, int which, int nch = 1) {
   xs.wait_epoch = (which == XS_A) ? h->epochA : h->epochB;
   if (h->capturing) { xs.wait_epoch -= (which == XS_A) ? h->cap_a0 : h->cap_b0; xs.wait_base = h->epoch_dev + which; }
   xs.err = h->err_dev;
+  if (!xs.trace_id) xs.trace_id = ++g_trace_n;
 }
+#if defined(SMO_XS_TRACE) && !defined(SMO_EMUL)
+// development only (not declared in the header): copy out / clear the hand-shake time-stamp trace
+extern "C" int smo_debug_xs_trace(unsigned long long* out, int reset) {
+  if (out) CUDA_TRY(cudaMemcpyFromSymbol(out, g_xs_trace, sizeof(unsigned long long) * XS_TRACE_SLOTS * 8));
+  if (reset) { void* d = nullptr; CUDA_TRY(cudaGetSymbolAddress(&d, g_xs_trace)); CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long) * XS_TRACE_SLOTS * 8)); }
+  return 0;
+}
+#endif
 
 // ---- TMA tensor maps of the x-spectral arrays ------------------------------------------------------------------------
 // An x-spectral array is [slices][Nh][ncols] complex (slices = fields x stored states, contiguous).  The fused x passes fetch a
@@ -941,7 +956,9 @@ template <int M> struct KdOps {
     }
     p.nwork = nf * p.nA * p.tilesB;
     prof_begin(h, PK_Y, st);
-    int rc = launch<FftPass<F, -1, true, TY>>(p, st, p.peer_mode ? h->push_waves : 1);
+    int rc;
+    if (p.peer_mode == 2 && (h->bulk_push & 2) && p.nB % TY == 0) rc = launch<FftPass<F, -1, true, TY, true>>(p, st, h->push_waves);   // staged rows, TMA bulk stores
+    else rc = launch<FftPass<F, -1, true, TY>>(p, st, p.peer_mode ? h->push_waves : 1);
     prof_end(h, PK_Y, st);
     return rc;
   }
@@ -1090,6 +1107,7 @@ template <int M> struct KdOps {
     if (h->nranks > 1) { p.seglen = h->nz; p.blk = (long long)h->nkx * h->Nc * h->nz; }
     if (h->peer_on && !h->peer_pull) {
       p.peer_mode = 1; p.peer_off = (long long)h->rank * p.blk;
+      p.bulk_push = (h->bulk_push & 1) ? 1 : 0;
       for (int f = 0; f < nf; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) p.peer_out[f][s2] = h->peer_p1t[f][s2];
     } else if (h->peer_on) {
       p.pull_mode = 1; p.pull_off = (long long)h->kx0 * h->Nc * h->nz;
@@ -1288,8 +1306,8 @@ static int pdl_on(const smo_kdyn* h) {
   if (h->nranks != 1 || h->two_streams != 0 || h->prof_which != 0) return 0;
   return h->pdl < 0 ? (h->N <= 64 ? 1 : 0) : (h->pdl ? 1 : 0);
 }
-static int graph_opts(const smo_kdyn* h) {
-  return (pdl_on(h) ? (int)(1u << 31) : 0) | ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
+static long long graph_opts(const smo_kdyn* h) {
+  return (pdl_on(h) ? (1ll << 31) : 0ll) | ((long long)(h->bulk_push & 3) << 32) | ((h->prof_which & 0xf) << 24) | (h->l2_hints ? 1 : 0) | (h->peer_pull ? 2 : 0) | (h->inkernel_sync ? 4 : 0) | (h->peer_on ? 8 : 0) |
          ((h->two_streams & 1) ? 16 : 0) | ((h->two_streams & 2) ? (1 << 29) : 0) | ((h->push_waves & 3) << 5) | (h->grid_acc ? 128 : 0) | (h->bulk_u ? (1 << 28) : 0) | (h->tma_sin ? (1 << 30) : 0) | ((h->chunks_fwd & 0xff) << 8) | ((h->chunks_adj & 0xff) << 16);
 }
 
@@ -1590,7 +1608,7 @@ extern "C" int smo_kdyn_create(smo_kdyn_t** out, int Npts, double L, int rank, i
   h->tma_sin = 1; h->tmc = nullptr; h->p2block = nullptr;     // (r2k: x-adj 196 -> 192 us at 128^3, 2.11 -> 1.94 ms at 256^3)
   h->grid_acc = 1; h->accg = nullptr; h->bulk_u = 1;     // (r2e: adjoint x pass 221 -> 196 us at 128^3, 2.46 -> 2.04 ms at 256^3)
   h->push_waves = 1; h->two_streams = 0; h->err_host = nullptr; h->err_dev = nullptr;
-  h->pdl = SMO_PDL_DEFAULT;
+  h->pdl = SMO_PDL_DEFAULT; h->bulk_push = SMO_BULK_PUSH_DEFAULT;
 #if !defined(SMO_EMUL)
   h->aux_stream = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
 #endif
@@ -1822,6 +1840,7 @@ extern "C" int smo_kdyn_set_option(smo_kdyn_t* h, int key, int value) {
     case SMO_OPT_GRID_ACC: h->grid_acc = value ? 1 : 0; return 0;
     case SMO_OPT_BULK_U: h->bulk_u = value ? 1 : 0; return 0;
     case SMO_OPT_TMA_SIN: h->tma_sin = value ? 1 : 0; return 0;
+    case SMO_OPT_BULK_PUSH: h->bulk_push = value & 3; return 0;
     case SMO_OPT_PDL: h->pdl = value < 0 ? -1 : (value ? 1 : 0); return 0;
     case 99:   // development only (WRONG RESULTS): point every peer buffer at the local one to time the kernels without NVLink traffic
       for (int f = 0; f < MAXF; ++f) for (int s2 = 0; s2 < h->nranks; ++s2) { h->peer_p1[f][s2] = h->p1[f]; h->peer_p1t[f][s2] = h->p1t[f]; }

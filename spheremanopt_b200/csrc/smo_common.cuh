@@ -104,6 +104,9 @@ SMO_HD void st_cplx_hint(cplx* p, double x, double y, unsigned long long pol) {
   p->x = x; p->y = y;
 #endif
 }
+// store of one complex value into a PEER GPU's memory (fused transposes).  Measured on 2 B200 (r2zb): st.relaxed.sys and st.wt
+// flavours run exactly like the plain store; a system fence after every tile costs +35 %.
+SMO_HD void st_peer(cplx* p, double x, double y) { p->x = x; p->y = y; }
 SMO_HD void cp_async_commit() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -156,6 +159,48 @@ SMO_HD void tma_load_3d(void* sdst, const SmoTensorMap* tm, int c0, int c1, int 
   (void)sdst; (void)tm; (void)c0; (void)c1; (void)c2; (void)bar;
 #endif
 }
+// TMA bulk STORE shared -> global (bulk async-group completion): one thread ships a contiguous staged block - also into a PEER
+// GPU's memory over NVLink (any generic global address) - through the async proxy.  The transposes pushed by the time-loop
+// kernels use it so that the remote stores do not sit in the SM's LSU queue in front of the local loads of the next tile.
+// Protocol: writers st.shared -> bulk_fence_smem() -> barrier -> issuer bulk_store()... bulk_commit(); the staging area may be
+// rewritten after bulk_wait_read(); the data is complete in (peer) memory after bulk_wait_all() + bulk_fence_global().
+SMO_HD void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+#else
+  memcpy(gdst, ssrc, bytes);
+#endif
+}
+SMO_HD void warp_sync() {
+#if defined(__CUDA_ARCH__)
+  __syncwarp();
+#endif
+}
+SMO_HD void bulk_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+SMO_HD void bulk_wait_read() {      // the committed bulk stores of this thread have finished READING shared memory
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+SMO_HD void bulk_wait_all() {       // ... have completed (their writes are performed)
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+}
+SMO_HD void bulk_fence_smem() {     // generic-proxy writes to shared memory -> visible to the async proxy (TMA)
+#if defined(__CUDA_ARCH__)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+SMO_HD void bulk_fence_global() {   // async-proxy writes to global memory -> ordered before this thread's later generic-proxy operations
+#if defined(__CUDA_ARCH__)
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+}
 SMO_HD void mbar_wait(unsigned long long* bar, unsigned parity) {
 #if defined(__CUDA_ARCH__)
   const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
@@ -171,9 +216,9 @@ SMO_HD void mbar_wait(unsigned long long* bar, unsigned parity) {
 //   * first waits until every source rank has published `wait_epoch` in this GPU's flag words (its inputs were stored
 //     into this GPU's memory by the peers' preceding kernel), and
 //   * after its last CTA has finished, publishes `sig_epoch` in every peer's flag word of this rank (its stores are
-//     complete and visible: per-CTA fence, completion counter, fence, flag stores).  sig_sys = 1: the data was stored
-//     into the peers' memory (push), the per-CTA fence must be system wide; 0: the data is local and the peers will read
-//     it through this GPU's L2 (pull), a device-wide fence is enough.
+//     complete and visible: per-CTA device-scope fence, completion counter, ONE system-scope fence in the last CTA -
+//     cumulative over all it acquired through the counter -, flag stores).  sig_sys = 1: the data was stored into the
+//     peers' memory (push); 0: the data is local and the peers will read it through this GPU's L2 (pull).
 // Measured on 2 B200 (tools/microbench/flag_latency.cu): flag word one way 1.0 us, every system fence +1 us (idle) to
 // +3.4 us (stores in flight); so the waiting side uses no fence at all - its loads are issued after the spin and a CTA
 // barrier, bypass L1 (cp.async.cg / peer addresses) and find the data already in the owning GPU's L2.
@@ -191,7 +236,17 @@ struct XSync {
   unsigned long long* sig_flags[MAXP];    // the peers' flag words of this (buffer, chunk): word [sig_rank] is this rank's
   unsigned int* counter;                  // local: CTAs of this launch that have finished
   unsigned int* err;                      // host-mapped word: set to 1 when a wait gave up (a peer died): results are invalid
+  int trace_id;                           // development builds (-DSMO_XS_TRACE): slot of this launch in the time-stamp trace, 0 = none
 };
+#if defined(SMO_XS_TRACE) && !defined(SMO_EMUL)
+// development only: per-launch time stamps (globaltimer, ns) of the hand-shake stages, read back with smo_debug_xs_trace()
+constexpr int XS_TRACE_SLOTS = 8192;
+__device__ unsigned long long g_xs_trace[XS_TRACE_SLOTS * 8];
+__device__ __forceinline__ unsigned long long xs_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define XS_TRACE(idx, val) do { if (p.xs.trace_id) g_xs_trace[(p.xs.trace_id % XS_TRACE_SLOTS) * 8 + (idx)] = (val); } while (0)
+#else
+#define XS_TRACE(idx, val) do { } while (0)
+#endif
 // Flag loads / stores of the hand-shake.  The waiter's load is an acquire at system scope (everything the peer stored
 // before its release-ordered flag store is visible to the loads that follow); the signaller's last CTA orders the whole
 // launch's stores with a system-wide fence before it publishes.  SMO_XSYNC_RELAXED restores the round-1 fast path (plain
@@ -297,6 +352,9 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const __grid_constant__ typename K::Params p) {
   extern __shared__ __align__(1024) unsigned char smo_smem[];     // (TMA swizzle patterns are functions of the shared-memory address)
   typename K::State st;
+#if defined(SMO_XS_TRACE)
+  if constexpr (has_xsync<K>::value) { if (blockIdx.x == 0 && threadIdx.x == 0) { XS_TRACE(0, xs_now()); XS_TRACE(6, (unsigned long long)gridDim.x); XS_TRACE(7, (unsigned long long)(K::THREADS * 1000 + K::NPHASES)); } }
+#endif
   if constexpr (is_v2<K>::value) {
     Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
     K::init(p, c, st);
@@ -319,10 +377,16 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const __
       __syncthreads();
     }
   }
+#if defined(SMO_XS_TRACE)
+  if constexpr (has_xsync<K>::value) { if (blockIdx.x == 0 && threadIdx.x == 0) XS_TRACE(1, xs_now()); }
+#endif
   for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
     for (int step = 0; step < p.nsteps; ++step)
       PhaseStep<K, 0, false>::run(p, work, step, (int)threadIdx.x, smo_smem, st);
   }
+#if defined(SMO_XS_TRACE)
+  if constexpr (has_xsync<K>::value) { if (blockIdx.x == 0 && threadIdx.x == 0) XS_TRACE(2, xs_now()); }
+#endif
   if constexpr (has_finish<K>::value) {   // per-CTA epilogue after the last work item (e.g. deterministic partial sums)
     __syncthreads();
     Ctx c; c.cta = (int)blockIdx.x; c.ncta = (int)gridDim.x; c.tid = (int)threadIdx.x; c.smem = smo_smem;
@@ -331,16 +395,30 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const __
     K::template finish<1>(p, c, st);
   }
   if constexpr (has_xsync<K>::value) {
+    bulk_wait_all();          // TMA bulk stores issued by this thread (staged peer pushes) are complete (no-op without any) ...
+    bulk_fence_global();      // ... and ordered before the fence / flag stores below
     if (p.xs.sig_n > 0) {
       __syncthreads();
       if (threadIdx.x == 0) {
         // the peers read (pull) or received (push) this launch's results: both need the stores ordered system-wide
 #if defined(SMO_XSYNC_RELAXED)
         if (p.xs.sig_sys) __threadfence_system(); else __threadfence();
+#elif defined(SMO_XSYNC_CTA_SYS)
+        __threadfence_system();      // (A/B: one system-scope fence per CTA, the protocol up to session r2zd)
 #else
-        __threadfence_system();
+        // Device-scope release of this CTA's stores: the CTA barrier above, this fence and the count below form a release pattern
+        // towards the last CTA (same GPU), whose ONE system-scope fence before the flag stores is cumulative over everything it
+        // acquired through the count (PTX memory model: causality order composes across scopes; the same reasoning by which a
+        // single thread's fence.sys publishes the stores its whole CTA made before a bar.sync).  A system-scope fence in EVERY CTA
+        // cost 10-15 us at the end of each pushing kernel (r2zc trace: it waits for the remote acknowledgements of the whole SM);
+        // the device-scope fence shortens the forward step on 2 GPUs from 159 to 148 us (r2zd).
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
         const unsigned int old = atomicAdd(p.xs.counter, 1u);
+#if defined(SMO_XS_TRACE)
+        if (blockIdx.x == 0) XS_TRACE(3, xs_now());
+        if (old == gridDim.x - 1) XS_TRACE(4, xs_now());
+#endif
         if (old == gridDim.x - 1) {
           *p.xs.counter = 0u;   // ready for the next launch
 #if defined(SMO_XSYNC_RELAXED)
@@ -350,6 +428,9 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) smo_kernel(const __
 #endif
           const unsigned long long val = p.xs.sig_epoch + (p.xs.sig_base ? *p.xs.sig_base : 0ull);
           for (int s = 0; s < p.xs.sig_n; ++s) xs_store_flag(p.xs.sig_flags[s] + p.xs.sig_rank, val);
+#if defined(SMO_XS_TRACE)
+          XS_TRACE(5, xs_now());
+#endif
         }
       }
     }

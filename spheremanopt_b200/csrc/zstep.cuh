@@ -51,6 +51,8 @@ struct ZParams {
   const cplx* peer_in[MAXF][MAXP];
   XSync xs;                 // cross-GPU wait / signal fused into the launch (smo_common.cuh)
   int l2_hints;             // 1: pencil lines are read evict_first and written evict_last, the coefficient state evict_first
+  int bulk_push;            // peer_mode 1: the output lines are staged in shared memory (per warp: [peer][line][seglen], in place of the
+                            // consumed exchange lines) and shipped with ONE TMA bulk store per (warp, peer) instead of 16-byte stores
 };
 
 template <class F, int T_> struct ZStep {
@@ -65,6 +67,8 @@ template <class F, int T_> struct ZStep {
   static constexpr int NPHASES = 9;
   static constexpr int MIN_BLOCKS = (F::RT > 16) ? 2 : SMO_ZS_MB;
   static constexpr bool WARP_OK = (32 % LP == 0);          // the threads of a line never straddle a warp
+  static constexpr int LW = WARP_OK ? ((32 / LP < T_) ? 32 / LP : T_) : 1;   // lines of one component a warp handles
+  static constexpr bool BULK_OK = WARP_OK && (T_ % LW == 0) && (LP * LW == 32);   // staged push: a warp owns LW whole lines of ONE component
   static constexpr int LAND = 3 * T_ * M, WORK = 3 * T_ * XP, STATE = 3 * T_ * PC;
   static constexpr size_t SMEM = (size_t)(LAND + WORK + STATE + M) * sizeof(cplx) + 2 * (size_t)M * sizeof(int) + 16;
   static_assert(XP >= PC, "compact coefficient line must fit into the exchange line");
@@ -184,6 +188,10 @@ template <class F, int T_> struct ZStep {
       // the landing line is consumed: stream in the same line of this CTA's next work item
       if (work + c.ncta < p.nwork) load_tile(p, work + c.ncta, c);
       cp_async_commit();
+      if (BULK_OK && p.bulk_push) {      // the previous tile's bulk stores (issued by this warp's first lane) have read the lines
+        if ((c.tid & 31) == 0) bulk_wait_read();
+        warp_sync();
+      }
       if (jj < R2 && fwd) {
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) Wk[jj * F::SK + k1] = make_double2(st.re[k1], st.im[k1]);
@@ -271,6 +279,44 @@ template <class F, int T_> struct ZStep {
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) Wk[jj * F::SK + k1] = make_double2(st.re[k1], st.im[k1]);
       }
+    } else if (BULK_OK && p.bulk_push && p.peer_mode == 1 && p.do_inv) {
+      // staged push: the LW lines of this warp go, segment by segment, to their owners with one bulk store per peer
+      const bool act = jj < R1 && live;
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < R2; ++j) {
+          const cplx v = Wk[j * F::SK + jj];
+          st.re[j] = v.x; st.im[j] = v.y;
+        }
+      }
+      warp_sync();                                   // every input of the warp's lines is in registers: the lines may be overwritten
+      const int t0 = t - t % LW;                       // first line of this warp
+      cplx* Sg = wrk(c.smem) + (f * T + t0) * XP;     // staging area = the warp's LW exchange lines, as [peer][line][seglen]
+      if (act) {
+        stage2<F, +1>(st.re, st.im);
+        const int* si = segidx(c.smem);
+        const int* sr = segrem(c.smem);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) {
+          const int k = jj + R1 * k2;
+          Sg[(si[k] * LW + (t - t0)) * p.seglen + sr[k]] = make_double2(st.re[k2], st.im[k2]);
+        }
+      }
+      bulk_fence_smem();
+      warp_sync();
+      if ((c.tid & 31) == 0) {
+        const int b0 = tile * T + t0;
+        const int nlive = imin(LW, p.nlines - b0);
+        if (nlive > 0) {
+          const int fo = 3 * trip + f;
+          const int nseg = M / p.seglen;
+          for (int s2 = 0; s2 < nseg; ++s2)
+            bulk_store(p.peer_out[fo][s2] + p.peer_off + (long long)b0 * p.line_stride, Sg + (size_t)s2 * LW * p.seglen,
+                       (unsigned)(nlive * p.seglen * sizeof(cplx)));
+          bulk_commit();
+        }
+      }
+      st.it++;
     } else {
       if (p.do_inv && jj < R1 && live) {
 #pragma unroll
@@ -287,7 +333,7 @@ template <class F, int T_> struct ZStep {
 #pragma unroll
           for (int k2 = 0; k2 < R2; ++k2) {
             const int k = jj + R1 * k2;
-            p.peer_out[fo][si[k]][p.peer_off + line + sr[k]] = make_double2(st.re[k2], st.im[k2]);
+            st_peer(&p.peer_out[fo][si[k]][p.peer_off + line + sr[k]], st.re[k2], st.im[k2]);
           }
         } else if (p.l2_hints) {
           cplx* dst = p.out[fo] + line;

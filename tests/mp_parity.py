@@ -28,6 +28,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cases = [(32, 6)] if world > 2 else [(16, 5), (32, 6), (64, 3)]      # (64: nz = 48 per rank at P = 2 -> chunked variants run)
+    if os.environ.get("MP_CASES"):      # e.g. "128:2" - the full grid of config 3 (the staged z-step push exists for 128^3 / 256^3 only)
+        cases = [tuple(int(v) for v in c.split(":")) for c in os.environ["MP_CASES"].split(",")]
     worst = 0.0
     for Npts, nit in cases:
         od = okd.domain_kdyn(Npts)
@@ -44,6 +46,8 @@ def main():
                     (True, 0, 0, 0, 1, 0, 1, 0), (False, 0, 0, 0, 1, 0, 1, 0),
                     (True, 1, 1, 0, 2, 1, 2, 0), (True, 1, 0, 0, 2, 1, 1, 0), (True, 1, 1, 0, 2, 0, 3, 0), (True, 1, 1, 1, 2, 1, 1, 0),
                     (True, 1, 1, 0, 1, 0, 1, 4), (True, 1, 1, 0, 2, 1, 2, 3), (False, 0, 0, 0, 1, 0, 1, 4))
+        if os.environ.get("MP_VARIANTS"):   # subset by index, e.g. "3,10"
+            variants = tuple(variants[int(i)] for i in os.environ["MP_VARIANTS"].split(","))
         for peer, ksync, fused, pull, chunks, two, waves, every in variants:
             if chunks > 1 and ((3 * Npts // 2) // world) % (8 * chunks):
                 continue     # (a z chunk must hold whole tiles of the y passes)

@@ -2,7 +2,7 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 --master-port 29511 tools/time_kdyn_mp.py [N] [nit]
 
-VARIANTS="waves,chunks,two_streams[,split];..." runs several tuning variants in ONE process (default "1,1,0"); split=1 adds
+VARIANTS="waves,chunks,two_streams[,split[,bulk_push]];..." runs several tuning variants in ONE process (default "1,1,0"); split=1 adds
 the per-kernel-class times.  J is printed for every variant (must agree between variants and GPU counts).
 """
 import ctypes as C
@@ -54,6 +54,9 @@ for spec in os.environ.get("VARIANTS", "1,1,0,1").split(";"):
     v = [int(x) for x in spec.split(",")]
     waves, chunks, two = v[0], v[1], v[2]
     split = v[3] if len(v) > 3 else 0
+    bulk = v[4] if len(v) > 4 else None
+    if bulk is not None:
+        lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_BULK_PUSH, bulk)
     lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_PUSH_WAVES, waves)
     lib.smo_kdyn_set_option(dom.h, _cabi.SMO_OPT_TWO_STREAMS, two)
     lib.smo_kdyn_set_chunks(dom.h, chunks, chunks)
@@ -61,7 +64,7 @@ for spec in os.environ.get("VARIANTS", "1,1,0,1").split(";"):
     for _ in range(3):
         f = kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)
     if rank == 0:
-        print("== P=%d N=%d waves=%d chunks=%d two_streams=%d: J=%.15e" % (world, N, waves, chunks, two, -f), flush=True)
+        print("== P=%d N=%d waves=%d chunks=%d two_streams=%d bulk_push=%s: J=%.15e" % (world, N, waves, chunks, two, bulk, -f), flush=True)
     for which in ((0, 0, 2, 3, 6, 7, 5) if split else (0, 0)):
         for fn, nm in ((kdyn.FWD_Solve_IVP_Lin, "fwd"), (kdyn.ADJ_Solve_IVP_Lin, "adj")):
             lib.smo_kdyn_profile_set(dom.h, which)
