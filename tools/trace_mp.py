@@ -44,8 +44,12 @@ for k, v in os.environ.items():
 if os.environ.get("GRAPH", "1") != "0":
     lib.smo_kdyn_use_graph(dom.h, 1)
 for _ in range(3):
-    kdyn.FWD_Solve_IVP_Lin(X, *args); kdyn.ADJ_Solve_IVP_Lin(X, *args)
+    f = kdyn.FWD_Solve_IVP_Lin(X, *args); gr = kdyn.ADJ_Solve_IVP_Lin(X, *args)
+gn = [float(ip(v.t)) for v in gr]
+if rank == 0:     # (same inputs as tools/time_kdyn_mp.py: J must agree with its runs at the same GPU count)
+    print("P=%d N=%d nit=%d: J=%.15e  <gB,gB>=%.15e  <gU,gU>=%.15e" % (world, N, nit, -f, gn[0], gn[1]), flush=True)
 NS = 8192
+out = []
 names = {128004: "y pass", 128006: "y-fwd (staged)", 96009: "z step"}
 for fn, nm in ((kdyn.FWD_Solve_IVP_Lin, "forward"), (kdyn.ADJ_Solve_IVP_Lin, "adjoint")):
     torch.cuda.synchronize()
@@ -64,7 +68,7 @@ for fn, nm in ((kdyn.FWD_Solve_IVP_Lin, "forward"), (kdyn.ADJ_Solve_IVP_Lin, "ad
         continue
     n = len(t)
     lo, hi = n // 4, 3 * n // 4      # the middle of the time loop
-    print("rank %d %s solve: %d traced launches, loop period %.2f us per step" % (rank, nm, n, (t[hi, 0] - t[lo, 0]) / 1e3 / ((hi - lo) / 3.0)), flush=True)
+    out.append("rank %d %s solve: %d traced launches, loop period %.2f us per step" % (rank, nm, n, (t[hi, 0] - t[lo, 0]) / 1e3 / ((hi - lo) / 3.0)))
     cls = {}
     for i in range(lo, hi):
         r = t[i]
@@ -74,9 +78,14 @@ for fn, nm in ((kdyn.FWD_Solve_IVP_Lin, "forward"), (kdyn.ADJ_Solve_IVP_Lin, "ad
         end = r[5] if sig else r[2]
         d = cls.setdefault(key, [])
         d.append((waits, work, (r[3] - r[2]) if r[3] > 0 else 0, (r[4] - r[2]) if sig else 0, (r[5] - r[4]) if sig else 0, end - r[0], t[i + 1, 0] - end, t[i + 1, 0] - r[0]))
-    print("   %-28s %6s | %8s %8s %8s %10s %8s | %8s %8s %8s" % ("kernel (signals?, waited?)", "n", "entry>go", "cta0work", "cta0fnc", "last-cta0", "lastflag", "total", "gap>next", "period"))
+    out.append("   %-28s %6s | %8s %8s %8s %10s %8s | %8s %8s %8s" % ("kernel (signals?, waited?)", "n", "entry>go", "cta0work", "cta0fnc", "last-cta0", "lastflag", "total", "gap>next", "period"))
     for key, d in sorted(cls.items()):
         a = np.array(d, dtype=np.float64).mean(axis=0) / 1e3
-        print("   %-28s %6d | %8.2f %8.2f %8.2f %10.2f %8.2f | %8.2f %8.2f %8.2f" % ("%s %s %s" % (names.get(key[0], key[0]), "signals" if key[1] else "", key[2]), len(d), *a), flush=True)
+        out.append("   %-28s %6d | %8.2f %8.2f %8.2f %10.2f %8.2f | %8.2f %8.2f %8.2f" % ("%s %s %s" % (names.get(key[0], key[0]), "signals" if key[1] else "", key[2]), len(d), *a))
+for r in sorted({0, world - 1}):
+    if rank == r:
+        print("\n".join(out), flush=True)
+    if world > 1:
+        dist.barrier()
 if world > 1:
     dist.destroy_process_group()
