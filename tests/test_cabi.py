@@ -26,6 +26,20 @@ def test_header_and_binding_agree():
     assert header_functions() == sorted(_cabi.SIGNATURES)
 
 
+def test_header_constants_and_binding_agree():
+    """every SMO_* integer constant of the header (flags, option keys) has the same value in the ctypes binding"""
+    from spheremanopt_b200 import _cabi
+    src = open(os.path.join(ROOT, "include", "smo_b200.h")).read()
+    consts = {k: int(v) for k, v in re.findall(r"^#define\s+(SMO_[A-Z0-9_]+)\s+(-?\d+)\b", src, flags=re.M)}
+    assert {"SMO_ADJOINT_CONTINUOUS", "SMO_COST_INTEGRATED", "SMO_OPT_PDL", "SMO_OPT_BULK_PUSH"} <= set(consts)
+    for k, v in consts.items():
+        if hasattr(_cabi, k):
+            assert getattr(_cabi, k) == v, k
+    opts = {k for k in consts if k.startswith("SMO_OPT_") and k != "SMO_OPT_FUSED_Z"}
+    assert opts <= set(dir(_cabi)), opts - set(dir(_cabi))
+    assert len({consts[k] for k in opts}) == len(opts)      # option keys are distinct
+
+
 def test_library_exports_every_declared_symbol(lib):
     from spheremanopt_b200 import _cabi
     out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
