@@ -756,7 +756,7 @@ enum { XS_NONE = 0, XS_A = 1, XS_B = 2 };
 static bool kernel_sync(const smo_kdyn* h) { return h->peer_on && h->inkernel_sync; }
 // the launch about to be issued publishes "buffer `which` (z chunk `chunk`) of every peer is filled by this rank" when it has
 // finished.  Epochs: one per transpose (all chunks of one transpose carry the same epoch; xs_next_epoch starts a new one).
-static int g_trace_n = 0;     // launch numbering of the development time-stamp trace (-DSMO_XS_TRACE)
+static std::atomic<int> g_trace_n{0};     // launch numbering of the development time-stamp trace (-DSMO_XS_TRACE)
 static unsigned long long xs_next_epoch(smo_kdyn* h, int which) { return (which == XS_A) ? ++h->epochA : ++h->epochB; }
 static void xs_signal(smo_kdyn* h, XSync& xs, int which, int chunk = 0, unsigned long long epoch = 0) {
   if (which == XS_NONE || !kernel_sync(h)) return;
