@@ -18,10 +18,12 @@ WANT = [("adjoint x pass 128^3 (XFused<Fac<16,12>, X_ADJ, GACC>)", "6XFusedINS_3
         ("forward x pass 128^3 (XFused<Fac<16,12>, X_FWD>)", "6XFusedINS_3FacILi16ELi12EEELi2ELb0ELb0EEE"),
         ("adjoint x pass 256^3 (XFusedH<Fac<16,12>, X_ADJ, GACC>)", "7XFusedHINS_3FacILi16ELi12EEELi3ELb0ELb1ELi2EEE"),
         ("fused z step 128^3 (ZStep<Fac<16,12>,2>)", "5ZStepINS_3FacILi16ELi12EEELi2EEE"),
-        ("y pass 128^3 inverse (FftPass<Fac<16,12>,+1,true,8>)", "7FftPassINS_3FacILi16ELi12EEELi1ELb1ELi8EEE"),
+        ("y pass 128^3 inverse (FftPass<Fac<16,12>,+1,true,8>)", "7FftPassINS_3FacILi16ELi12EEELi1ELb1ELi8ELb0EEE"),
+        ("y pass 128^3 forward, staged bulk push (FftPass<Fac<16,12>,-1,true,8,STAGE>)", "7FftPassINS_3FacILi16ELi12EEELin1ELb1ELi8ELb1EEE"),
         ("SH23 adjoint, ensembles (Sh23Adj<Fac<16,16>,4,8>)", "7Sh23AdjINS_3FacILi16ELi16EEELi4ELi8EEE"),
         ("Inner_Product (VecKernel<V_DOT>)", "9VecKernelILi0EEE")]
-KEYS = ["DFMA", "DADD", "DMUL", "LDS", "STS", "LDGSTS", "UBLKCP", "UTMALDG", "SYNCS", "LDG", "STG", "CCTL", "BAR", "WARPSYNC", "SHFL", "MEMBAR", "ATOMG", "RED"]
+KEYS = ["DFMA", "DADD", "DMUL", "LDS", "STS", "LDGSTS", "UBLKCP", "UTMALDG", "SYNCS", "LDG", "STG", "CCTL", "BAR", "WARPSYNC", "SHFL", "MEMBAR", "ATOMG", "RED",
+        "ACQBULK", "PREEXIT"]     # (ACQBULK / PREEXIT = griddepcontrol.wait / .launch_dependents: programmatic dependent launch)
 
 names = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", names)
