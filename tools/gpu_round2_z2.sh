@@ -1,5 +1,6 @@
 #!/bin/bash
 # session r2z2: PDL trigger placement (early / late) and explicit start stagger of the y / z kernels, one GPU
+# (historical record: the -DSMO_PDL_LATE / -DSMO_STAGGER_NS build switches these variants used were measured and removed again)
 O=gpurun_out; mkdir -p $O
 for v in late stag500 stag1000; do
   echo "== variant $v" >> $O/r2z2_pdl_variants.txt

@@ -1,5 +1,6 @@
 #!/bin/bash
 # session r2zb (2 GPUs): why do the pushing kernels take local time + transfer time?  peer-store flavours / per-tile system fences
+# (historical record: the -DSMO_PEER_ST / -DSMO_PUSH_TILE_FENCE build switches these variants used were measured and removed again)
 O=gpurun_out; mkdir -p $O
 P=${P:-2}
 L=$O/r2zb_push_variants_p$P.txt

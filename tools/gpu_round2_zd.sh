@@ -1,5 +1,6 @@
 #!/bin/bash
 # session r2zd (P GPUs): per-CTA device-scope fence + one system fence in the last CTA (variant) - parity and hand-shake trace
+# (historical record: the variant of this session - device-scope fence per CTA - became the default; -DSMO_XSYNC_CTA_SYS restores the old protocol)
 O=gpurun_out; mkdir -p $O
 P=${P:-2}
 L=$O/r2zd_gpufence_p$P.txt
