@@ -145,11 +145,16 @@ class SH23Ensemble(Rendezvous):
         self.store = torch.zeros(n, self.row, dtype=torch.float64, device=domain.device)
         self.tag = [None] * n
         self._tmp = {}
+        self._scratch = None
         super().__init__(n, self._f, self._grad, self._ip)
 
     def _tmp_store(self, k):
+        # group sizes drift between 1 and n during a run: every size is a VIEW of the first k rows of one scratch block (a store
+        # of its own per distinct size would add up to ~n^2/2 rows - tens of GB for 512 instances of config 1)
+        if self._scratch is None:
+            self._scratch = torch.zeros(self.n * self.row, dtype=torch.float64, device=self.domain.device)
         if k not in self._tmp:
-            self._tmp[k] = self._sh.GEN_BUFFER(self.domain, self.nit, batch=k)
+            self._tmp[k] = self._sh.SnapshotStore(self.domain, self.nit, batch=k, buf=self._scratch[:k * self.row])
         return self._tmp[k]
 
     def _stack(self, vecs):

@@ -70,11 +70,16 @@ class SnapshotStore(dict):
     product reads; written from the registers of the forward solve) + the coefficients of the final state.  ``['A_fwd']``
     converts back (one r2c launch per state) and returns a host copy in the reference's [Npts/2, N_SUB_ITERS+1] orientation."""
 
-    def __init__(self, domain, n_iters, batch=1):
+    def __init__(self, domain, n_iters, batch=1, buf=None):
         super().__init__()
         self.domain, self.n_iters, self.batch = domain, int(n_iters), int(batch)
         self.inst_bytes = domain.lib.smo_sh23_snapshot_bytes(domain.h, self.n_iters)
-        self.buf = torch.zeros(self.inst_bytes * self.batch // 8, dtype=torch.float64, device=domain.device)
+        n = self.inst_bytes * self.batch // 8
+        if buf is None:
+            buf = torch.zeros(n, dtype=torch.float64, device=domain.device)
+        elif buf.dtype != torch.float64 or buf.dim() != 1 or buf.numel() != n or not buf.is_contiguous():
+            raise ValueError("snapshot store over an existing buffer: need a contiguous float64 vector of %d entries" % n)
+        self.buf = buf       # (instances are contiguous rows: the first k rows of a larger store are a k-instance store)
         self.valid = False
 
     def ptr(self):

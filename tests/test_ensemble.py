@@ -131,6 +131,36 @@ def test_sh23_ensemble_on_gpu():
         assert np.allclose(out[i][1], ho, rtol=1e-9, atol=0)
 
 
+def test_sh23_ensemble_group_stores_are_views_of_one_scratch_block():
+    """group sizes drift during a run: the temporary store of every size is a view of the first k instance rows of ONE block
+    (host logic only: a stub domain on the CPU, no library call besides the size query)"""
+    import torch
+    from spheremanopt_b200 import sh23
+    from spheremanopt_b200.ensemble import SH23Ensemble
+
+    class _Lib:
+        def smo_sh23_snapshot_bytes(self, h, nit):
+            return 8 * ((nit + 1) * 16 + 4)
+
+    class _Dom:
+        lib, h, device, M = _Lib(), None, torch.device("cpu"), 16
+
+    K, nit = 6, 3
+    ens = SH23Ensemble(K, _Dom(), 0.1, nit)
+    row = ens.row
+    assert row == (nit + 1) * 16 + 4 and ens.store.shape == (K, row)
+    s2, s6, s2b = ens._tmp_store(2), ens._tmp_store(6), ens._tmp_store(2)
+    assert s2 is s2b and s2.batch == 2 and s6.batch == 6
+    assert s2.buf.numel() == 2 * row and s6.buf.numel() == 6 * row
+    assert s2.buf.data_ptr() == s6.buf.data_ptr() == ens._scratch.data_ptr() and ens._scratch.numel() == K * row
+    s6.buf.view(6, row)[1].fill_(7.0)
+    assert float(s2.buf.view(2, row)[1].min()) == 7.0 and float(s2.buf.view(2, row)[0].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        sh23.SnapshotStore(_Dom(), nit, batch=2, buf=torch.zeros(2 * row + 1, dtype=torch.float64))
+    own = sh23.SnapshotStore(_Dom(), nit, batch=3)
+    assert own.buf.numel() == 3 * row and own.buf.data_ptr() != ens._scratch.data_ptr()
+
+
 def test_rendezvous_scales_to_many_workers():
     """256 workers with drifting call sequences: per-worker wake-ups, no lost wake-up, every call served exactly once"""
     from spheremanopt_b200.ensemble import Rendezvous
