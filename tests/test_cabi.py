@@ -58,6 +58,26 @@ def test_library_is_sm100a_cuda():
     assert "sm_100a" in r.stdout
 
 
+def test_every_phase_kernel_waits_for_its_grid_dependency():
+    """programmatic dependent launches (SMO_OPT_PDL) are only correct if EVERY kernel a time loop can launch blocks in
+    griddepcontrol.wait before it touches its predecessor's results: static check of the SASS (ACQBULK = griddepcontrol.wait,
+    PREEXIT = griddepcontrol.launch_dependents) of every smo_kernel<> instantiation"""
+    from spheremanopt_b200 import _cabi
+    r = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    funcs = re.split(r"\n\s*Function : ", r.stdout)[1:]
+    kernels = [f for f in funcs if "smo_kernel" in f.split("\n", 1)[0]]
+    assert len(kernels) > 50
+    for f in kernels:
+        name = f.split("\n", 1)[0]
+        assert "ACQBULK" in f and "PREEXIT" in f, name
+        # the wait comes before the first global store / bulk store / atomic of the kernel
+        first = {op: f.find(op) for op in ("ACQBULK", " STG", "UBLKCP.G.S", " ATOMG", " RED.")}
+        for op, pos in first.items():
+            assert op == "ACQBULK" or pos < 0 or pos > first["ACQBULK"], (name, op)
+
+
 def test_argument_errors_without_gpu(lib):
     import ctypes as C
     h = C.c_void_p()
